@@ -1,0 +1,641 @@
+// fpb_capi.cu -- C ABI (include/flashpca_b200.h) over the sm_100a kernels.
+//
+// Host-side state of one staged genotype matrix (or SNP shard of one):
+//   d_bed    nsnps x pitch bytes   staged 2-bit genotypes (see fpb_kernels.cuh)
+//   d_lut    nsnps x double4       per-SNP code -> standardised value table
+//   d_meansd nsnps x 2             Data::X_meansd (data.cpp:290-291)
+//   d_t, d_coef                    per-op scratch (X'x and the prod coefficients)
+// No CPU fallback exists: if CUDA is unusable every entry point fails.
+#include "../../include/flashpca_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <errno.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "fpb_irlm.cuh"
+#include "fpb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Tiling {
+  int W = 1;
+  uint32_t block = 256, chunks = 1, splits = 1, snps_per_split = 1;
+};
+
+// minimal NCCL surface, resolved with dlopen so the library has no link-time
+// dependency on NCCL (single-GPU users never load it).
+typedef struct { char internal[128]; } NcclUniqueId;
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      err = std::string("cannot load NCCL: ") + dlerror();
+      return false;
+    }
+    GetUniqueId = (int (*)(NcclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(
+        lib, "ncclAllReduce");
+    CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+      err = "NCCL library lacks required symbols";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+}  // namespace
+
+struct fpb_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t n = 0, nsnps = 0, np = 0, pitch = 0;
+  int stand_method = 0;
+  int sm_count = 148;
+  uint8_t* d_bed = nullptr;
+  double4* d_lut = nullptr;
+  double* d_meansd = nullptr;
+  double* d_t = nullptr;
+  double4* d_coef = nullptr;
+  double* d_c0 = nullptr;
+  double* d_in = nullptr;   // host-pointer API staging (grown on demand)
+  double* d_out = nullptr;
+  size_t in_cap = 0, out_cap = 0;
+  double trace = 0.0;
+  Tiling tl;
+  NcclComm comm = nullptr;
+  int nranks = 1, rank = 0;
+  uint64_t launches = 0;
+  std::vector<float> op_ms;
+  std::string err;
+};
+
+#define FPB_FAIL(h, msg)                           \
+  do {                                             \
+    g_err = (msg);                                 \
+    if (h) (h)->err = g_err;                       \
+    return 1;                                      \
+  } while (0)
+
+#define FPB_CUDA(h, call)                                                                 \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      g_err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;        \
+      if (h) (h)->err = g_err;                                                            \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+namespace {
+
+Tiling pick_tiling(uint64_t words_per_row, uint64_t nsnps, int sm_count) {
+  Tiling t;
+  t.W = words_per_row >= 4096 ? 2 : 1;
+  const uint32_t cands[] = {256, 224, 192, 160, 128};
+  uint64_t best_waste = ~0ull;
+  for (uint32_t b : cands) {
+    uint64_t per = (uint64_t)b * t.W;
+    uint64_t chunks = (words_per_row + per - 1) / per;
+    uint64_t waste = chunks * per - words_per_row;
+    if (waste < best_waste) {
+      best_waste = waste;
+      t.block = b;
+      t.chunks = (uint32_t)chunks;
+    }
+  }
+  uint64_t target = (uint64_t)sm_count * 8;
+  uint64_t splits = std::max<uint64_t>(1, target / t.chunks);
+  splits = std::min<uint64_t>(splits, std::max<uint64_t>(1, nsnps / 64));
+  splits = std::min<uint64_t>(splits, 65535);
+  t.snps_per_split = (uint32_t)((nsnps + splits - 1) / splits);
+  t.splits = (uint32_t)((nsnps + t.snps_per_split - 1) / t.snps_per_split);
+  return t;
+}
+
+int alloc_common(fpb_handle* h, uint64_t n, uint64_t nsnps, int stand_method, int device) {
+  if (n == 0 || nsnps == 0) FPB_FAIL(h, "empty genotype matrix (N == 0 or nsnps == 0)");
+  if (nsnps > 0xFFFFFFF0ull) FPB_FAIL(h, "too many SNPs for one handle");
+  if (stand_method != FPB_STANDARDISE_BINOM && stand_method != FPB_STANDARDISE_BINOM2)
+    FPB_FAIL(h, std::string("unknown standardisation method: ") + std::to_string(stand_method));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    FPB_FAIL(h, std::string("no usable CUDA device (flashpca_b200 has no CPU fallback): ") +
+                    cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) FPB_FAIL(h, "invalid CUDA device ordinal");
+  h->device = device;
+  FPB_CUDA(h, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FPB_CUDA(h, cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->n = n;
+  h->nsnps = nsnps;
+  h->np = (n + 3) / 4;
+  h->pitch = (h->np + 15) / 16 * 16;
+  h->stand_method = stand_method;
+  FPB_CUDA(h, cudaMalloc(&h->d_bed, h->pitch * nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_lut, sizeof(double4) * nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_meansd, sizeof(double) * 2 * nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_t, sizeof(double) * nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_coef, sizeof(double4) * nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_c0, sizeof(double)));
+  h->tl = pick_tiling(h->pitch / 4, nsnps, h->sm_count);
+  return 0;
+}
+
+// padding fix-up + first-visit statistics (data.cpp:257-322) + trace
+int finish_create(fpb_handle* h, const double* preloaded_meansd) {
+  uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
+  fpb::k_fix_padding<<<gb, 256, 0, h->stream>>>(h->d_bed, h->nsnps, h->n, h->pitch);
+  h->launches++;
+  if (preloaded_meansd)
+    FPB_CUDA(h, cudaMemcpyAsync(h->d_meansd, preloaded_meansd, sizeof(double) * 2 * h->nsnps,
+                                cudaMemcpyHostToDevice, h->stream));
+  double* d_tracej = nullptr;
+  FPB_CUDA(h, cudaMalloc(&d_tracej, sizeof(double) * h->nsnps));
+  uint32_t gs = (uint32_t)((h->nsnps * 32 + 255) / 256);
+  fpb::k_snp_stats<<<gs, 256, 0, h->stream>>>(h->d_bed, h->nsnps, h->pitch, h->stand_method,
+                                              preloaded_meansd != nullptr, h->d_meansd, h->d_lut,
+                                              d_tracej);
+  h->launches++;
+  std::vector<double> tr(h->nsnps);
+  FPB_CUDA(h, cudaMemcpyAsync(tr.data(), d_tracej, sizeof(double) * h->nsnps,
+                              cudaMemcpyDeviceToHost, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  FPB_CUDA(h, cudaFree(d_tracej));
+  FPB_CUDA(h, cudaGetLastError());
+  double s = 0.0;
+  for (double v : tr) s += v;  // SNP order, like the block loop of svdwide.cpp:44-61
+  h->trace = s;
+  return 0;
+}
+
+int ensure_staging(fpb_handle* h, size_t in_elems, size_t out_elems) {
+  if (in_elems > h->in_cap) {
+    if (h->d_in) cudaFree(h->d_in);
+    h->d_in = nullptr;
+    FPB_CUDA(h, cudaMalloc(&h->d_in, sizeof(double) * in_elems));
+    h->in_cap = in_elems;
+  }
+  if (out_elems > h->out_cap) {
+    if (h->d_out) cudaFree(h->d_out);
+    h->d_out = nullptr;
+    FPB_CUDA(h, cudaMalloc(&h->d_out, sizeof(double) * out_elems));
+    h->out_cap = out_elems;
+  }
+  return 0;
+}
+
+// t (nsnps) = X' x
+void launch_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
+  const Tiling& t = h->tl;
+  cudaMemsetAsync(d_t, 0, sizeof(double) * h->nsnps, h->stream);
+  dim3 grid(t.chunks, t.splits);
+  if (t.W == 1)
+    fpb::k_crossprod<1><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n,
+                                                          (uint32_t)h->nsnps, t.snps_per_split,
+                                                          d_x, h->d_lut, d_t);
+  else
+    fpb::k_crossprod<2><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n,
+                                                          (uint32_t)h->nsnps, t.snps_per_split,
+                                                          d_x, h->d_lut, d_t);
+  h->launches++;
+}
+
+// y (N) = X v
+void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
+  const Tiling& t = h->tl;
+  uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
+  fpb::k_prod_coef<<<gb, 256, 0, h->stream>>>(h->d_lut, d_v, (uint32_t)h->nsnps, h->d_coef);
+  fpb::k_sum_a0<<<1, 1024, 0, h->stream>>>(h->d_coef, (uint32_t)h->nsnps, h->d_c0);
+  if (t.splits > 1) cudaMemsetAsync(d_y, 0, sizeof(double) * h->n, h->stream);
+  dim3 grid(t.chunks, t.splits);
+  if (t.W == 1)
+    fpb::k_prod<1><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n, (uint32_t)h->nsnps,
+                                                     t.snps_per_split, h->d_coef, h->d_c0, d_y);
+  else
+    fpb::k_prod<2><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n, (uint32_t)h->nsnps,
+                                                     t.snps_per_split, h->d_coef, h->d_c0, d_y);
+  h->launches += 3;
+}
+
+int allreduce(fpb_handle* h, double* d_buf, size_t count) {
+  if (!h->comm) return 0;
+  int rc = g_nccl.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
+  if (rc != 0)
+    FPB_FAIL(h, std::string("ncclAllReduce failed: ") +
+                    (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  return 0;
+}
+
+int check_launch(fpb_handle* h) {
+  FPB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fpb_abi_version(void) { return 1; }
+
+const char* fpb_last_error(const fpb_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int fpb_create(fpb_handle** out, const unsigned char* bed_payload, uint64_t n, uint64_t nsnps,
+               int stand_method, const double* preloaded_meansd, int device) {
+  if (!out || !bed_payload) FPB_FAIL((fpb_handle*)nullptr, "null argument");
+  *out = nullptr;
+  fpb_handle* h = new fpb_handle();
+  if (alloc_common(h, n, nsnps, stand_method, device) ||
+      [&]() -> int {
+        FPB_CUDA(h, cudaMemcpy2DAsync(h->d_bed, h->pitch, bed_payload, h->np, h->np, nsnps,
+                                      cudaMemcpyHostToDevice, h->stream));
+        return 0;
+      }() ||
+      finish_create(h, preloaded_meansd)) {
+    g_err = h->err;
+    fpb_destroy(h);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+int fpb_create_from_file(fpb_handle** out, const char* bed_path, uint64_t n, uint64_t snp_begin,
+                         uint64_t snp_count, int stand_method, const double* preloaded_meansd,
+                         int device) {
+  if (!out || !bed_path) FPB_FAIL((fpb_handle*)nullptr, "null argument");
+  *out = nullptr;
+  if (n == 0) FPB_FAIL((fpb_handle*)nullptr, "empty genotype matrix (N == 0 or nsnps == 0)");
+  FILE* f = fopen(bed_path, "rb");
+  if (!f)
+    FPB_FAIL((fpb_handle*)nullptr, std::string("[Data::read_bed] Error reading file ") + bed_path +
+                                       ", error " + strerror(errno));
+  // data.cpp:163-170: len = filesize - 3, np = ceil(N/4), nsnps = len / np
+  fseeko(f, 0, SEEK_END);
+  uint64_t fsz = (uint64_t)ftello(f);
+  uint64_t len = fsz >= 3 ? fsz - 3 : 0;
+  uint64_t np = (n + 3) / 4;
+  uint64_t file_snps = len / np;
+  if (snp_begin > file_snps) snp_begin = file_snps;
+  if (snp_count == 0 || snp_begin + snp_count > file_snps) snp_count = file_snps - snp_begin;
+  fpb_handle* h = new fpb_handle();
+  int rc = alloc_common(h, n, snp_count, stand_method, device);
+  if (!rc) {
+    rc = [&]() -> int {
+      // double-buffered pinned staging, 32 MiB slabs of whole SNP rows
+      uint64_t rows_per_slab = std::max<uint64_t>(1, (32ull << 20) / np);
+      unsigned char* pin[2] = {nullptr, nullptr};
+      cudaEvent_t ev[2];
+      for (int b = 0; b < 2; b++) {
+        FPB_CUDA(h, cudaMallocHost(&pin[b], rows_per_slab * np));
+        FPB_CUDA(h, cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+      }
+      fseeko(f, (off_t)(3 + np * snp_begin), SEEK_SET);
+      int b = 0;
+      int failed = 0;
+      for (uint64_t r = 0; r < snp_count && !failed; r += rows_per_slab, b ^= 1) {
+        uint64_t rows = std::min(rows_per_slab, snp_count - r);
+        cudaEventSynchronize(ev[b]);
+        if (fread(pin[b], 1, rows * np, f) != rows * np) {
+          h->err = std::string("[Data::read_bed] Error reading file ") + bed_path;
+          failed = 1;
+          break;
+        }
+        if (cudaMemcpy2DAsync(h->d_bed + r * h->pitch, h->pitch, pin[b], np, np, rows,
+                              cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+          h->err = "CUDA error staging bed";
+          failed = 1;
+        }
+        cudaEventRecord(ev[b], h->stream);
+      }
+      cudaStreamSynchronize(h->stream);
+      for (int q = 0; q < 2; q++) {
+        cudaFreeHost(pin[q]);
+        cudaEventDestroy(ev[q]);
+      }
+      return failed;
+    }();
+  }
+  fclose(f);
+  if (!rc) rc = finish_create(h, preloaded_meansd);
+  if (rc) {
+    g_err = h->err;
+    fpb_destroy(h);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+int fpb_create_synthetic(fpb_handle** out, uint64_t n, uint64_t nsnps, uint64_t snp_offset,
+                         const unsigned char* pop_of_individual, const uint32_t* thresholds,
+                         uint32_t npop, uint32_t missing_threshold, uint64_t seed,
+                         int stand_method, int device) {
+  if (!out || !pop_of_individual || !thresholds)
+    FPB_FAIL((fpb_handle*)nullptr, "null argument");
+  *out = nullptr;
+  fpb_handle* h = new fpb_handle();
+  int rc = alloc_common(h, n, nsnps, stand_method, device);
+  if (!rc) {
+    rc = [&]() -> int {
+      uint8_t* d_pop = nullptr;
+      uint32_t* d_thr = nullptr;
+      FPB_CUDA(h, cudaMalloc(&d_pop, n));
+      FPB_CUDA(h, cudaMalloc(&d_thr, sizeof(uint32_t) * (size_t)npop * nsnps));
+      FPB_CUDA(h, cudaMemcpyAsync(d_pop, pop_of_individual, n, cudaMemcpyHostToDevice, h->stream));
+      FPB_CUDA(h, cudaMemcpyAsync(d_thr, thresholds, sizeof(uint32_t) * (size_t)npop * nsnps,
+                                  cudaMemcpyHostToDevice, h->stream));
+      uint64_t total = nsnps * h->np;
+      uint64_t blocks = (total + 255) / 256;
+      if (blocks > 0x7FFFFFFFull) FPB_FAIL(h, "synthetic matrix too large for one launch");
+      fpb::k_synth_bed<<<(uint32_t)blocks, 256, 0, h->stream>>>(
+          h->d_bed, nsnps, n, h->pitch, snp_offset, d_pop, d_thr, missing_threshold, seed);
+      h->launches++;
+      FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+      cudaFree(d_pop);
+      cudaFree(d_thr);
+      return 0;
+    }();
+  }
+  if (!rc) rc = finish_create(h, nullptr);
+  if (rc) {
+    g_err = h->err;
+    fpb_destroy(h);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+void fpb_destroy(fpb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->d_bed);
+  cudaFree(h->d_lut);
+  cudaFree(h->d_meansd);
+  cudaFree(h->d_t);
+  cudaFree(h->d_coef);
+  cudaFree(h->d_c0);
+  cudaFree(h->d_in);
+  cudaFree(h->d_out);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+uint64_t fpb_rows(const fpb_handle* h) { return h ? h->n : 0; }
+uint64_t fpb_cols(const fpb_handle* h) { return h ? h->n : 0; }
+uint64_t fpb_nsnps(const fpb_handle* h) { return h ? h->nsnps : 0; }
+void* fpb_stream(const fpb_handle* h) { return h ? (void*)h->stream : nullptr; }
+uint64_t fpb_launch_count(const fpb_handle* h) { return h ? h->launches : 0; }
+
+int fpb_get_meansd(fpb_handle* h, double* out_meansd) {
+  if (!h || !out_meansd) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  FPB_CUDA(h, cudaMemcpyAsync(out_meansd, h->d_meansd, sizeof(double) * 2 * h->nsnps,
+                              cudaMemcpyDeviceToHost, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int fpb_get_trace(fpb_handle* h, double* out_trace) {
+  if (!h || !out_trace) FPB_FAIL(h, "null argument");
+  *out_trace = h->trace;
+  return 0;
+}
+
+int fpb_get_bed(fpb_handle* h, unsigned char* out_payload) {
+  if (!h || !out_payload) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  FPB_CUDA(h, cudaMemcpy2DAsync(out_payload, h->np, h->d_bed, h->pitch, h->np, h->nsnps,
+                                cudaMemcpyDeviceToHost, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int fpb_sync(fpb_handle* h) {
+  if (!h) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  FPB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------ device-pointer ops -------------------------
+
+int fpb_crossprod_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, double* d_y) {
+  if (!h || !d_m || !d_y || k == 0) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  for (uint32_t c = 0; c < k; c++)
+    launch_crossprod(h, d_m + (uint64_t)c * h->n, d_y + (uint64_t)c * h->nsnps);
+  return check_launch(h);
+}
+
+int fpb_prod_multi_dev(fpb_handle* h, const double* d_v, uint32_t k, double* d_y) {
+  if (!h || !d_v || !d_y || k == 0) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  for (uint32_t c = 0; c < k; c++)
+    launch_prod(h, d_v + (uint64_t)c * h->nsnps, d_y + (uint64_t)c * h->n);
+  if (check_launch(h)) return 1;
+  return allreduce(h, d_y, (size_t)h->n * k);
+}
+
+int fpb_perform_op_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, double* d_y) {
+  if (!h || !d_m || !d_y || k == 0) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  for (uint32_t c = 0; c < k; c++) {
+    launch_crossprod(h, d_m + (uint64_t)c * h->n, h->d_t);
+    launch_prod(h, h->d_t, d_y + (uint64_t)c * h->n);
+  }
+  if (check_launch(h)) return 1;
+  return allreduce(h, d_y, (size_t)h->n * k);
+}
+
+int fpb_perform_op_dev(fpb_handle* h, const double* d_x, double* d_y) {
+  return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+}
+
+// ------------------------------ host-pointer ops ---------------------------
+
+static int host_op(fpb_handle* h, const double* in, uint32_t k, double* out, uint64_t in_rows,
+                   uint64_t out_rows, int (*dev_fn)(fpb_handle*, const double*, uint32_t, double*)) {
+  if (!h || !in || !out || k == 0) FPB_FAIL(h, "null argument");
+  if (in == out) FPB_FAIL(h, "input and output must not alias");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  if (ensure_staging(h, (size_t)in_rows * k, (size_t)out_rows * k)) return 1;
+  FPB_CUDA(h, cudaMemcpyAsync(h->d_in, in, sizeof(double) * in_rows * k, cudaMemcpyHostToDevice,
+                              h->stream));
+  if (dev_fn(h, h->d_in, k, h->d_out)) return 1;
+  FPB_CUDA(h, cudaMemcpyAsync(out, h->d_out, sizeof(double) * out_rows * k,
+                              cudaMemcpyDeviceToHost, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int fpb_perform_op_multi(fpb_handle* h, const double* m_in, uint32_t k, double* y_out) {
+  return host_op(h, m_in, k, y_out, h ? h->n : 0, h ? h->n : 0, fpb_perform_op_multi_dev);
+}
+int fpb_perform_op(fpb_handle* h, const double* x_in, double* y_out) {
+  return fpb_perform_op_multi(h, x_in, 1, y_out);
+}
+int fpb_crossprod_multi(fpb_handle* h, const double* m_in, uint32_t k, double* y_out) {
+  return host_op(h, m_in, k, y_out, h ? h->n : 0, h ? h->nsnps : 0, fpb_crossprod_multi_dev);
+}
+int fpb_crossprod(fpb_handle* h, const double* x_in, double* y_out) {
+  return fpb_crossprod_multi(h, x_in, 1, y_out);
+}
+int fpb_prod_multi(fpb_handle* h, const double* v_in, uint32_t k, double* y_out) {
+  return host_op(h, v_in, k, y_out, h ? h->nsnps : 0, h ? h->n : 0, fpb_prod_multi_dev);
+}
+int fpb_prod(fpb_handle* h, const double* v_in, double* y_out) {
+  return fpb_prod_multi(h, v_in, 1, y_out);
+}
+
+// ------------------------------ multi-GPU ----------------------------------
+
+int fpb_comm_unique_id(unsigned char id_out[128]) {
+  if (!id_out) FPB_FAIL((fpb_handle*)nullptr, "null argument");
+  if (!g_nccl.load(g_err)) return 1;
+  NcclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) FPB_FAIL((fpb_handle*)nullptr, "ncclGetUniqueId failed");
+  memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+int fpb_comm_init(fpb_handle* h, const unsigned char id_in[128], int nranks, int rank) {
+  if (!h || !id_in) FPB_FAIL(h, "null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) FPB_FAIL(h, "invalid rank / nranks");
+  if (!g_nccl.load(g_err)) {
+    h->err = g_err;
+    return 1;
+  }
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  NcclUniqueId id;
+  memcpy(id.internal, id_in, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (rc != 0)
+    FPB_FAIL(h, std::string("ncclCommInitRank failed: ") +
+                    (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  h->nranks = nranks;
+  h->rank = rank;
+  return 0;
+}
+
+// ------------------------------ whole solve --------------------------------
+
+int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double tol,
+            double* evals_out, double* evecs_out, uint32_t* nconv_out, uint32_t* nops_out,
+            uint32_t* niter_out) {
+  if (!h) FPB_FAIL(h, "null argument");
+  if (nev < 1 || ncv <= nev || ncv > h->n || ncv > (uint32_t)fpb::kMaxNcv)
+    FPB_FAIL(h, "invalid nev/ncv (need 1 <= nev < ncv <= min(N, 128))");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  h->op_ms.clear();
+  std::vector<cudaEvent_t> evs;
+  int op_rc = 0;
+  auto op = [&](const double* d_in, double* d_out) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, h->stream);
+    op_rc |= fpb_perform_op_dev(h, d_in, d_out);
+    cudaEventRecord(b, h->stream);
+    evs.push_back(a);
+    evs.push_back(b);
+  };
+  fpb::Irlm solver(h->n, nev, ncv, h->stream, op);
+  fpb::IrlmResult res;
+  solver.run(maxiter, tol, res);
+  cudaStreamSynchronize(h->stream);
+  for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+    h->op_ms.push_back(ms);
+    cudaEventDestroy(evs[i]);
+    cudaEventDestroy(evs[i + 1]);
+  }
+  if (op_rc) return 1;
+  if (!solver.error.empty()) FPB_FAIL(h, solver.error);
+  FPB_CUDA(h, cudaGetLastError());
+  if (evals_out) memcpy(evals_out, res.evals.data(), sizeof(double) * nev);
+  if (evecs_out) {
+    if (ensure_staging(h, 0, (size_t)h->n * nev)) return 1;
+    solver.eigenvectors(h->d_out);
+    FPB_CUDA(h, cudaMemcpyAsync(evecs_out, h->d_out, sizeof(double) * h->n * nev,
+                                cudaMemcpyDeviceToHost, h->stream));
+    FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (nconv_out) *nconv_out = res.nconv;
+  if (nops_out) *nops_out = res.nops;
+  if (niter_out) *niter_out = res.niter;
+  FPB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+uint32_t fpb_pca_op_times(const fpb_handle* h, float* ms_out, uint32_t cap) {
+  if (!h || !ms_out) return 0;
+  uint32_t m = (uint32_t)std::min<size_t>(cap, h->op_ms.size());
+  for (uint32_t i = 0; i < m; i++) ms_out[i] = h->op_ms[i];
+  return m;
+}
+
+int fpb_time_perform_op(fpb_handle* h, const double* d_x, double* d_y, uint32_t reps,
+                        float* ms_per_op_out, float* ms_kernels_out) {
+  if (!h || !d_x || !d_y || reps == 0) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  cudaEvent_t e0, e1, e2, e3;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+  FPB_CUDA(h, cudaEventRecord(e0, h->stream));
+  for (uint32_t r = 0; r < reps; r++)
+    if (fpb_perform_op_dev(h, d_x, d_y)) return 1;
+  FPB_CUDA(h, cudaEventRecord(e1, h->stream));
+  FPB_CUDA(h, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_per_op_out) *ms_per_op_out = ms / reps;
+  if (ms_kernels_out) {
+    // one more op with events around each dominant kernel
+    cudaEventRecord(e0, h->stream);
+    launch_crossprod(h, d_x, h->d_t);
+    cudaEventRecord(e1, h->stream);
+    cudaEventRecord(e2, h->stream);
+    launch_prod(h, h->d_t, d_y);
+    cudaEventRecord(e3, h->stream);
+    FPB_CUDA(h, cudaEventSynchronize(e3));
+    cudaEventElapsedTime(&ms_kernels_out[0], e0, e1);
+    cudaEventElapsedTime(&ms_kernels_out[1], e2, e3);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+  FPB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// fpb_irlm.cuh -- device-resident implicitly restarted Lanczos.
+//
+// Follows the schedule of Spectra 0.8.1 SymEigsSolver<double, LARGEST_ALGE, Op>
+// as flashpca drives it (randompca.cpp:174-190: nev = ndim, ncv = 2*ndim+1,
+// init() then compute(maxiter, tol)).  Spectra is a third-party header library
+// that is not part of the flashpca tree; the steps below restate its published
+// algorithm (ARPACK dsaup2-style IRLM with full re-orthogonalisation).
+//
+// The Krylov basis V (N x ncv), residual f and work vector w stay in HBM; the
+// ncv x ncv projected matrix H lives on the host.  All reductions are two-stage
+// with a fixed order (no atomics) so that SNP-sharded ranks, which run this
+// driver redundantly on identical all-reduced vectors, stay bit-identical and
+// take the same convergence decisions.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <functional>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace fpb {
+
+constexpr int kMaxNcv = 128;      // columns handled by the tall-skinny kernels
+constexpr int kRowsPerBlock = 2048;
+
+// partial[g * m + c] = sum over rows of block g of V[r + c*ld] * f[r]
+__global__ void __launch_bounds__(256)
+k_gemv_t_partial(const double* __restrict__ V, uint64_t ld, uint32_t m,
+                 const double* __restrict__ f, uint64_t n, double* __restrict__ partial) {
+  __shared__ double sh[8][kMaxNcv];
+  const int RPT = kRowsPerBlock / 256;
+  uint64_t r0 = (uint64_t)blockIdx.x * kRowsPerBlock + threadIdx.x;
+  double fr[RPT];
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    uint64_t r = r0 + (uint64_t)q * 256;
+    fr[q] = r < n ? f[r] : 0.0;
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t c = 0; c < m; c++) {
+    const double* col = V + (uint64_t)c * ld;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < RPT; q++) {
+      uint64_t r = r0 + (uint64_t)q * 256;
+      if (r < n) s += col[r] * fr[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sh[warp][c] = s;
+  }
+  __syncthreads();
+  for (uint32_t c = threadIdx.x; c < m; c += 256) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += sh[w][c];
+    partial[(uint64_t)blockIdx.x * m + c] = s;
+  }
+}
+
+__global__ void k_gemv_t_final(const double* __restrict__ partial, uint32_t nblocks, uint32_t m,
+                               double* __restrict__ out) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  double s = 0.0;
+  for (uint32_t g = 0; g < nblocks; g++) s += partial[(uint64_t)g * m + c];
+  out[c] = s;
+}
+
+// f[r] -= sum_c V[r + c*ld] * h[c]
+__global__ void __launch_bounds__(256)
+k_gemv_n_sub(const double* __restrict__ V, uint64_t ld, uint32_t m, const double* __restrict__ h,
+             double* __restrict__ f, uint64_t n) {
+  __shared__ double hs[kMaxNcv];
+  for (uint32_t c = threadIdx.x; c < m; c += blockDim.x) hs[c] = h[c];
+  __syncthreads();
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double s = 0.0;
+  for (uint32_t c = 0; c < m; c++) s += V[r + (uint64_t)c * ld] * hs[c];
+  f[r] -= s;
+}
+
+// f = w - b * vprev - a * vcur   (vprev may be null when b is unused)
+__global__ void k_resid(const double* __restrict__ w, const double* __restrict__ vprev, double b,
+                        const double* __restrict__ vcur, double a, double* __restrict__ f,
+                        uint64_t n) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double v = w[r] - a * vcur[r];
+  if (vprev) v -= b * vprev[r];
+  f[r] = v;
+}
+
+// out = a * x + b * y  (y may be null)
+__global__ void k_axpby(double a, const double* x, double b, const double* y, double* out,
+                        uint64_t n) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double v = a * x[r];
+  if (y) v += b * y[r];
+  out[r] = v;
+}
+
+// out[r, c] = sum_k V[r, k] * Q[k + c*ldq], c < nc, k < m.  The small factor
+// (m x nc <= ncv x ncv) sits in shared memory; one thread per row keeps its V
+// row in registers.
+template <int MAXM>
+__global__ void __launch_bounds__(128)
+k_tall_times_small(const double* __restrict__ V, uint64_t ld, uint32_t m,
+                   const double* __restrict__ Q, uint32_t ldq, uint32_t nc,
+                   double* __restrict__ out, uint64_t ldo, uint64_t n) {
+  extern __shared__ double qs[];
+  for (uint32_t e = threadIdx.x; e < m * nc; e += blockDim.x) {
+    uint32_t c = e / m, k = e - c * m;
+    qs[e] = Q[k + (uint64_t)c * ldq];
+  }
+  __syncthreads();
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double vr[MAXM];
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) vr[k] = (uint32_t)k < m ? V[r + (uint64_t)k * ld] : 0.0;
+  for (uint32_t c = 0; c < nc; c++) {
+    const double* qc = qs + c * m;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXM; k++)
+      if ((uint32_t)k < m) s += vr[k] * qc[k];
+    out[r + (uint64_t)c * ldo] = s;
+  }
+}
+
+// Fallback for m > MAXM of the register-cached kernel above.
+__global__ void __launch_bounds__(128)
+k_tall_times_small_generic(const double* __restrict__ V, uint64_t ld, uint32_t m,
+                           const double* __restrict__ Q, uint32_t ldq, uint32_t nc,
+                           double* __restrict__ out, uint64_t ldo, uint64_t n) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (uint32_t c = 0; c < nc; c++) {
+    double s = 0.0;
+    for (uint32_t k = 0; k < m; k++) s += V[r + (uint64_t)k * ld] * Q[k + (uint64_t)c * ldq];
+    out[r + (uint64_t)c * ldo] = s;
+  }
+}
+
+// ------------------------------- host algebra -------------------------------
+
+// Spectra SimpleRandom<double>: Park-Miller LCG, a = 16807, m = 2^31 - 1,
+// seed 0 -> 1, uniform(-0.5, 0.5).
+inline void simple_random_vec(std::vector<double>& out, uint64_t n, unsigned long seed) {
+  const unsigned long m = 2147483647UL, a = 16807UL;
+  unsigned long r = seed ? (seed & m) : 1UL;
+  out.resize(n);
+  for (uint64_t i = 0; i < n; i++) {
+    r = (a * r) % m;
+    out[i] = (double)r / (double)m - 0.5;
+  }
+}
+
+// Eigen-decomposition of a symmetric tridiagonal matrix by implicit-shift QL.
+// d: diagonal (n), e: sub-diagonal (e[i] couples i and i+1; e[n-1] unused),
+// z: n x n column-major, returns eigenvectors in columns.  false on failure.
+inline bool tridiag_eigen(int n, std::vector<double>& d, std::vector<double>& e,
+                          std::vector<double>& z) {
+  z.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) z[(size_t)i * n + i] = 1.0;
+  e[n - 1] = 0.0;
+  for (int l = 0; l < n; l++) {
+    int iter = 0, m;
+    do {
+      for (m = l; m < n - 1; m++) {
+        double dd = fabs(d[m]) + fabs(d[m + 1]);
+        if (fabs(e[m]) <= DBL_EPSILON * dd) break;
+      }
+      if (m != l) {
+        if (iter++ == 200) return false;
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + (g >= 0 ? fabs(r) : -fabs(r)));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = m - 1; i >= l; i--) {
+          double f = s * e[i], b = c * e[i];
+          r = hypot(f, g);
+          e[i + 1] = r;
+          if (r == 0.0) {
+            d[i + 1] -= p;
+            e[m] = 0.0;
+            break;
+          }
+          s = f / r;
+          c = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * b;
+          p = s * r;
+          d[i + 1] = g + p;
+          g = c * r - b;
+          for (int k = 0; k < n; k++) {
+            double* zi = &z[(size_t)i * n + k];
+            double* zi1 = &z[(size_t)(i + 1) * n + k];
+            f = *zi1;
+            *zi1 = s * (*zi) + c * f;
+            *zi = c * (*zi) - s * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p;
+        e[l] = g;
+        e[m] = 0.0;
+      }
+    } while (m != l);
+  }
+  return true;
+}
+
+// One shifted QR step on the (tridiagonal, symmetric) projected matrix:
+// H - mu I = QR;  H <- RQ + mu I;  Qacc <- Qacc * Q.   (Spectra restart())
+inline void tridiag_qr_step(int n, std::vector<double>& H, double mu, std::vector<double>& Qacc) {
+  auto A = [&](int r, int c) -> double& { return H[(size_t)c * n + r]; };
+  std::vector<double> cs(n), sn(n);
+  for (int i = 0; i < n; i++) A(i, i) -= mu;
+  for (int i = 0; i < n - 1; i++) {
+    double x = A(i, i), y = A(i + 1, i);
+    double r = hypot(x, y), c = 1.0, s = 0.0;
+    if (r > 0.0) {
+      c = x / r;
+      s = y / r;
+    }
+    cs[i] = c;
+    sn[i] = s;
+    for (int k = 0; k < n; k++) {
+      double a = A(i, k), b = A(i + 1, k);
+      A(i, k) = c * a + s * b;
+      A(i + 1, k) = -s * a + c * b;
+    }
+  }
+  for (int i = 0; i < n - 1; i++) {
+    double c = cs[i], s = sn[i];
+    for (int k = 0; k < n; k++) {
+      double a = A(k, i), b = A(k, i + 1);
+      A(k, i) = c * a + s * b;
+      A(k, i + 1) = -s * a + c * b;
+      double qa = Qacc[(size_t)i * n + k], qb = Qacc[(size_t)(i + 1) * n + k];
+      Qacc[(size_t)i * n + k] = c * qa + s * qb;
+      Qacc[(size_t)(i + 1) * n + k] = -s * qa + c * qb;
+    }
+  }
+  // keep H exactly symmetric tridiagonal, as Spectra's TridiagQR::matrix_RQ does
+  std::vector<double> dg(n), sb(n);
+  for (int i = 0; i < n; i++) dg[i] = A(i, i) + mu;
+  for (int i = 0; i + 1 < n; i++) sb[i] = A(i + 1, i);
+  std::fill(H.begin(), H.end(), 0.0);
+  for (int i = 0; i < n; i++) A(i, i) = dg[i];
+  for (int i = 0; i + 1 < n; i++) {
+    A(i + 1, i) = sb[i];
+    A(i, i + 1) = sb[i];
+  }
+}
+
+struct IrlmResult {
+  std::vector<double> evals;  // nev, descending, only the first nconv_sorted are converged-flagged
+  std::vector<char> conv;     // nev flags after sorting
+  uint32_t nconv = 0, nops = 0, niter = 0;
+};
+
+// Device-vector IRLM.  `op(d_in, d_out)` enqueues A * in -> out on `stream`.
+class Irlm {
+ public:
+  Irlm(uint64_t n, uint32_t nev, uint32_t ncv, cudaStream_t stream,
+       std::function<void(const double*, double*)> op)
+      : n_(n), nev_(nev), ncv_(ncv), stream_(stream), op_(std::move(op)) {}
+  ~Irlm() { release(); }
+
+  // Runs init() + compute(maxit, tol).  On return d_V()/ritz vectors can be
+  // combined with eigenvectors().
+  void run(uint32_t maxit, double tol, IrlmResult& res);
+  // evecs (N x nev, column-major, device) = V * ritz_vec, sorted like evals.
+  void eigenvectors(double* d_out);
+  std::string error;
+
+ private:
+  void alloc();
+  void release();
+  void gemv_t(const double* V, uint32_t m, const double* f, double* host_out);
+  double norm(const double* f) {
+    double s;
+    gemv_t(f, 1, f, &s);
+    return sqrt(s);
+  }
+  void factorize_from(uint32_t from_k, uint32_t to_m);
+  void retrieve_ritzpair();
+  // d_out (N x nc) = V (N x ncv) * dQ (ncv x nc)
+  void tall_times_small(const double* dQ, uint32_t nc, double* d_out) {
+    if (ncv_ <= 48)
+      k_tall_times_small<48><<<grid1d(128), 128, sizeof(double) * ncv_ * nc, stream_>>>(
+          dV_, n_, ncv_, dQ, ncv_, nc, d_out, n_, n_);
+    else
+      k_tall_times_small_generic<<<grid1d(128), 128, 0, stream_>>>(dV_, n_, ncv_, dQ, ncv_, nc,
+                                                                   d_out, n_, n_);
+  }
+  double& H(uint32_t r, uint32_t c) { return H_[(size_t)c * ncv_ + r]; }
+  double* col(uint32_t i) { return dV_ + (uint64_t)i * n_; }
+  uint32_t grid1d(uint32_t bs) const { return (uint32_t)((n_ + bs - 1) / bs); }
+
+  uint64_t n_;
+  uint32_t nev_, ncv_;
+  cudaStream_t stream_;
+  std::function<void(const double*, double*)> op_;
+  double *dV_ = nullptr, *dF_ = nullptr, *dW_ = nullptr, *dVs_ = nullptr, *dPartial_ = nullptr,
+         *dSmall_ = nullptr, *dQ_ = nullptr;
+  uint32_t nblocks_ = 0;
+  std::vector<double> H_, ritz_val_, ritz_est_, ritz_vec_;  // ritz_vec_: ncv x nev
+  double beta_ = 0.0;
+  uint32_t nops_ = 0;
+  std::vector<uint32_t> order_;
+};
+
+inline void Irlm::alloc() {
+  nblocks_ = (uint32_t)((n_ + kRowsPerBlock - 1) / kRowsPerBlock);
+  cudaMalloc(&dV_, sizeof(double) * n_ * ncv_);
+  cudaMalloc(&dVs_, sizeof(double) * n_ * ncv_);
+  cudaMalloc(&dF_, sizeof(double) * n_);
+  cudaMalloc(&dW_, sizeof(double) * n_);
+  cudaMalloc(&dPartial_, sizeof(double) * (size_t)nblocks_ * ncv_);
+  cudaMalloc(&dSmall_, sizeof(double) * ncv_);
+  cudaMalloc(&dQ_, sizeof(double) * ncv_ * ncv_);
+  cudaMemsetAsync(dV_, 0, sizeof(double) * n_ * ncv_, stream_);
+  H_.assign((size_t)ncv_ * ncv_, 0.0);
+}
+
+inline void Irlm::release() {
+  cudaFree(dV_); cudaFree(dVs_); cudaFree(dF_); cudaFree(dW_);
+  cudaFree(dPartial_); cudaFree(dSmall_); cudaFree(dQ_);
+  dV_ = dVs_ = dF_ = dW_ = dPartial_ = dSmall_ = dQ_ = nullptr;
+}
+
+inline void Irlm::gemv_t(const double* V, uint32_t m, const double* f, double* host_out) {
+  k_gemv_t_partial<<<nblocks_, 256, 0, stream_>>>(V, n_, m, f, n_, dPartial_);
+  k_gemv_t_final<<<(m + 63) / 64, 64, 0, stream_>>>(dPartial_, nblocks_, m, dSmall_);
+  cudaMemcpyAsync(host_out, dSmall_, sizeof(double) * m, cudaMemcpyDeviceToHost, stream_);
+  cudaStreamSynchronize(stream_);
+}
+
+inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
+  if (to_m <= from_k) return;
+  const double eps = DBL_EPSILON, near0 = DBL_MIN * 10.0;
+  double beta = norm(dF_);
+  for (uint32_t c = from_k; c < ncv_; c++)
+    for (uint32_t r = 0; r < ncv_; r++) H(r, c) = 0.0;
+  for (uint32_t r = from_k; r < ncv_; r++)
+    for (uint32_t c = 0; c < from_k; c++) H(r, c) = 0.0;
+  std::vector<double> Vf(ncv_), rnd;
+  for (uint32_t i = from_k; i < to_m; i++) {
+    bool restart = false;
+    if (beta < near0) {
+      // invariant subspace: new random direction orthogonal to V[:, :i]
+      simple_random_vec(rnd, n_, 2UL * i);
+      cudaMemcpyAsync(dF_, rnd.data(), sizeof(double) * n_, cudaMemcpyHostToDevice, stream_);
+      gemv_t(dV_, i, dF_, Vf.data());
+      cudaMemcpyAsync(dSmall_, Vf.data(), sizeof(double) * i, cudaMemcpyHostToDevice, stream_);
+      k_gemv_n_sub<<<grid1d(256), 256, 0, stream_>>>(dV_, n_, i, dSmall_, dF_, n_);
+      beta = norm(dF_);
+      restart = true;
+    }
+    k_axpby<<<grid1d(256), 256, 0, stream_>>>(1.0 / beta, dF_, 0.0, nullptr, col(i), n_);
+    H(i, i - 1) = restart ? 0.0 : beta;
+    op_(col(i), dW_);
+    nops_++;
+    double Hii;
+    gemv_t(col(i), 1, dW_, &Hii);
+    H(i - 1, i) = H(i, i - 1);
+    H(i, i) = Hii;
+    k_resid<<<grid1d(256), 256, 0, stream_>>>(dW_, restart ? nullptr : col(i - 1), H(i, i - 1),
+                                              col(i), Hii, dF_, n_);
+    beta = norm(dF_);
+    const uint32_t i1 = i + 1;
+    gemv_t(dV_, i1, dF_, Vf.data());
+    auto maxabs = [&]() {
+      double m = 0.0;
+      for (uint32_t c = 0; c < i1; c++) m = std::max(m, fabs(Vf[c]));
+      return m;
+    };
+    double ortho_err = maxabs();
+    int count = 0;
+    while (count < 5 && ortho_err > eps * beta) {
+      if (beta < near0) {
+        cudaMemsetAsync(dF_, 0, sizeof(double) * n_, stream_);
+        beta = 0.0;
+        break;
+      }
+      cudaMemcpyAsync(dSmall_, Vf.data(), sizeof(double) * i1, cudaMemcpyHostToDevice, stream_);
+      k_gemv_n_sub<<<grid1d(256), 256, 0, stream_>>>(dV_, n_, i1, dSmall_, dF_, n_);
+      H(i - 1, i) += Vf[i - 1];
+      H(i, i - 1) = H(i - 1, i);
+      H(i, i) += Vf[i];
+      beta = norm(dF_);
+      gemv_t(dV_, i1, dF_, Vf.data());
+      ortho_err = maxabs();
+      count++;
+    }
+  }
+  beta_ = beta;
+}
+
+inline void Irlm::retrieve_ritzpair() {
+  std::vector<double> d(ncv_), e(ncv_, 0.0), z;
+  for (uint32_t i = 0; i < ncv_; i++) d[i] = H(i, i);
+  for (uint32_t i = 0; i + 1 < ncv_; i++) e[i] = H(i + 1, i);
+  if (!tridiag_eigen((int)ncv_, d, e, z)) error = "tridiagonal eigen-decomposition failed";
+  std::vector<uint32_t> ind(ncv_);
+  std::iota(ind.begin(), ind.end(), 0u);
+  std::stable_sort(ind.begin(), ind.end(), [&](uint32_t a, uint32_t b) { return d[a] > d[b]; });
+  ritz_val_.resize(ncv_);
+  ritz_est_.resize(ncv_);
+  ritz_vec_.assign((size_t)ncv_ * nev_, 0.0);
+  for (uint32_t i = 0; i < ncv_; i++) {
+    ritz_val_[i] = d[ind[i]];
+    ritz_est_[i] = z[(size_t)ind[i] * ncv_ + (ncv_ - 1)];
+  }
+  for (uint32_t i = 0; i < nev_; i++)
+    for (uint32_t r = 0; r < ncv_; r++) ritz_vec_[(size_t)i * ncv_ + r] = z[(size_t)ind[i] * ncv_ + r];
+}
+
+inline void Irlm::run(uint32_t maxit, double tol, IrlmResult& res) {
+  const double eps = DBL_EPSILON, near0 = DBL_MIN * 10.0, eps23 = pow(eps, 2.0 / 3.0);
+  alloc();
+  nops_ = 0;
+  // init(): v0 = SimpleRandom(0) normalised; w = A v0; H00 = v0.w; f = w - H00 v0
+  std::vector<double> r0;
+  simple_random_vec(r0, n_, 0);
+  cudaMemcpyAsync(dF_, r0.data(), sizeof(double) * n_, cudaMemcpyHostToDevice, stream_);
+  double vnorm = norm(dF_);
+  k_axpby<<<grid1d(256), 256, 0, stream_>>>(1.0 / vnorm, dF_, 0.0, nullptr, col(0), n_);
+  op_(col(0), dW_);
+  nops_++;
+  double h00;
+  gemv_t(col(0), 1, dW_, &h00);
+  H(0, 0) = h00;
+  k_resid<<<grid1d(256), 256, 0, stream_>>>(dW_, nullptr, 0.0, col(0), h00, dF_, n_);
+
+  factorize_from(1, ncv_);
+  retrieve_ritzpair();
+
+  uint32_t nconv = 0, it = 0;
+  std::vector<char> conv(nev_, 0);
+  for (it = 0; it < maxit; it++) {
+    nconv = 0;
+    for (uint32_t i = 0; i < nev_; i++) {
+      double thresh = tol * std::max(eps23, fabs(ritz_val_[i]));
+      double resid = fabs(ritz_est_[i]) * beta_;
+      conv[i] = resid < thresh;
+      nconv += conv[i];
+    }
+    if (nconv >= nev_) break;
+    // nev_adjusted(): ARPACK dsaup2 rule
+    uint32_t nev_new = nev_;
+    for (uint32_t i = nev_; i < ncv_; i++)
+      if (fabs(ritz_est_[i]) < near0) nev_new++;
+    nev_new += std::min(nconv, (ncv_ - nev_new) / 2);
+    if (nev_new == 1 && ncv_ >= 6) nev_new = ncv_ / 2;
+    else if (nev_new == 1 && ncv_ > 2) nev_new = 2;
+    if (nev_new > ncv_ - 1) nev_new = ncv_ - 1;
+    const uint32_t k = nev_new;
+    // restart(k): shifts = unwanted Ritz values
+    std::vector<double> Q((size_t)ncv_ * ncv_, 0.0);
+    for (uint32_t i = 0; i < ncv_; i++) Q[(size_t)i * ncv_ + i] = 1.0;
+    for (uint32_t i = k; i < ncv_; i++) tridiag_qr_step((int)ncv_, H_, ritz_val_[i], Q);
+    // V[:, :k+1] <- V Q[:, :k+1]
+    cudaMemcpyAsync(dQ_, Q.data(), sizeof(double) * ncv_ * ncv_, cudaMemcpyHostToDevice, stream_);
+    tall_times_small(dQ_, k + 1, dVs_);
+    cudaMemcpyAsync(dV_, dVs_, sizeof(double) * n_ * (k + 1), cudaMemcpyDeviceToDevice, stream_);
+    // f <- f * Q(ncv-1, k-1) + V[:, k] * H(k, k-1)
+    k_axpby<<<grid1d(256), 256, 0, stream_>>>(Q[(size_t)(k - 1) * ncv_ + (ncv_ - 1)], dF_,
+                                              H(k, k - 1), col(k), dF_, n_);
+    factorize_from(k, ncv_);
+    retrieve_ritzpair();
+    if (!error.empty()) break;
+  }
+  // sort_ritzpair(LARGEST_ALGE) over the first nev
+  order_.resize(nev_);
+  std::iota(order_.begin(), order_.end(), 0u);
+  std::stable_sort(order_.begin(), order_.end(),
+                   [&](uint32_t a, uint32_t b) { return ritz_val_[a] > ritz_val_[b]; });
+  res.evals.resize(nev_);
+  res.conv.resize(nev_);
+  for (uint32_t i = 0; i < nev_; i++) {
+    res.evals[i] = ritz_val_[order_[i]];
+    res.conv[i] = conv[order_[i]];
+  }
+  res.nconv = nconv;
+  res.nops = nops_;
+  res.niter = it + 1;
+}
+
+inline void Irlm::eigenvectors(double* d_out) {
+  std::vector<double> R((size_t)ncv_ * nev_);
+  for (uint32_t i = 0; i < nev_; i++)
+    for (uint32_t r = 0; r < ncv_; r++)
+      R[(size_t)i * ncv_ + r] = ritz_vec_[(size_t)order_[i] * ncv_ + r];
+  cudaMemcpyAsync(dQ_, R.data(), sizeof(double) * ncv_ * nev_, cudaMemcpyHostToDevice, stream_);
+  tall_times_small(dQ_, nev_, d_out);
+  cudaStreamSynchronize(stream_);
+}
+
+}  // namespace fpb

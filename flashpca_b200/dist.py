@@ -1,0 +1,48 @@
+"""SNP-sharded multi-GPU plumbing: one process per GPU, torch.distributed for
+rendezvous and host-side collectives; the per-op all-reduce itself runs inside
+the native library on its NCCL communicator (fpb_comm_init).
+
+X X' x = sum_g X_g X_g' x over disjoint contiguous SNP ranges -- the block sum
+of svdwide.cpp:48-59, distributed."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+
+def shard_range(nsnps: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous SNP range [j0, j1) of `rank`, balanced by count."""
+    base, rem = divmod(nsnps, world)
+    j0 = rank * base + min(rank, rem)
+    return j0, j0 + base + (1 if rank < rem else 0)
+
+
+def gather_meansd(local_meansd: np.ndarray, nsnps: int, world: int, rank: int) -> np.ndarray:
+    """Concatenate per-shard (mean, sd) rows into the full nsnps x 2 table
+    (Data::X_meansd is column-local, data.cpp:290-291)."""
+    import torch
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, np.ascontiguousarray(local_meansd))
+    out = np.concatenate(parts, axis=0)
+    assert out.shape[0] == nsnps
+    return np.asfortranarray(out)
+
+
+def attach_nccl(op, world: int, rank: int) -> None:
+    """Create the library-side NCCL communicator: rank 0 makes the unique id,
+    torch.distributed broadcasts it, every rank joins."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    lib = _lib.load()
+    uid = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        _lib.check(lib.fpb_comm_unique_id(uid.ctypes.data))
+    t = torch.from_numpy(uid)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    uid = t.cpu().numpy()
+    _lib.check(lib.fpb_comm_init(op.h, uid.ctypes.data, world, rank), op.h)

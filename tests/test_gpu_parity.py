@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs (bit-exact for the integer-derived statistics; the
+floating-point tolerances are written next to each assertion)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, load_fixture
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# y = X X' x: both sides sum ~N*P doubles in different orders (SURVEY.md section 8e:
+# "expect ~1e-15 relative differences"); bound used throughout:
+OP_RTOL = 1e-12
+
+
+def _mk(payload, n, p, **kw):
+    from flashpca_b200 import SVDWideOnline
+    return SVDWideOnline(payload=payload, n=n, nsnps=p, **kw)
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _pack(codes):
+    """(n, p) raw codes -> packed payload with zero pad bits."""
+    n, p = codes.shape
+    npb = (n + 3) // 4
+    padded = np.zeros((p, npb * 4), dtype=np.uint8)
+    padded[:, :n] = codes.T
+    q = padded.reshape(p, npb, 4)
+    return (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(
+        np.uint8).ravel()
+
+
+@pytest.mark.parametrize("name", ["data_chr1", "hapmap3"])
+@pytest.mark.parametrize("stand", [O.STANDARDISE_BINOM2, O.STANDARDISE_BINOM])
+def test_fixture_operator_family(native_lib, name, stand):
+    _, payload, n, p = load_fixture(name)
+    op = _mk(payload, n, p, stand_method=stand)
+    orc = O.COracle(payload, n, p, stand)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(n)
+    y_ref = orc.perform_op(x, 0)            # also fills oracle statistics
+    assert np.array_equal(op.meansd(), orc.meansd())          # bit-exact mean / sd
+    assert abs(op.trace - orc.trace) <= 1e-12 * orc.trace
+    assert (op.rows(), op.cols()) == (n, n)
+    assert _relerr(op.perform_op(x), y_ref) <= OP_RTOL
+    assert _relerr(op.crossprod(x), orc.crossprod(x)) <= OP_RTOL
+    v = rng.standard_normal(p)
+    assert _relerr(op.prod(v), orc.prod(v)) <= OP_RTOL
+    m = rng.standard_normal((n, 3))
+    assert _relerr(op.perform_op_mat(m), orc.perform_op(m, 0)) <= OP_RTOL
+    assert _relerr(op.crossprod2(m), orc.crossprod(m, 0)) <= OP_RTOL
+    w = rng.standard_normal((p, 2))
+    assert _relerr(op.prod3(w), orc.prod(w, 0)) <= OP_RTOL
+    # the staged bytes are the file's bytes for every real individual
+    assert np.array_equal(O.dense_codes(op.bed_payload(), n, p), O.dense_codes(payload, n, p))
+    op.close()
+
+
+def test_reference_block_order_vs_one_pass(native_lib):
+    """Upstream accumulates block by block (svdwide.cpp:48-59); the GPU sums in
+    one pass.  Same result within OP_RTOL for the reference's block sizes."""
+    _, payload, n, p = load_fixture("data_chr1")
+    op = _mk(payload, n, p)
+    x = np.random.default_rng(5).standard_normal(n)
+    y = op.perform_op(x)
+    for bs in (1129, 302, 37):
+        assert _relerr(y, O.COracle(payload, n, p).perform_op(x, bs)) <= OP_RTOL
+
+
+@pytest.mark.parametrize("n,p", [(1, 3), (3, 1), (4, 5), (63, 9), (64, 64), (65, 130), (1000, 17),
+                                 (4099, 257), (16384 + 5, 40)])
+def test_ragged_shapes(native_lib, n, p):
+    """N not a multiple of 4/16/64 (pad genotypes must contribute 0), tiny and
+    ragged shapes, heavy missingness."""
+    rng = np.random.default_rng(n * 1000 + p)
+    codes = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(n, p),
+                       p=[0.15, 0.1, 0.35, 0.4])
+    payload = _pack(codes)
+    # dirty pad bits: upstream ignores whatever sits there (it loops i < N)
+    if n % 4:
+        npb = (n + 3) // 4
+        pl = payload.reshape(p, npb)
+        pl[:, -1] |= np.uint8((0xFF << (2 * (n % 4))) & 0xFF)
+    op = _mk(payload, n, p)
+    orc = O.COracle(payload, n, p)
+    x = rng.standard_normal(n)
+    y_ref = orc.perform_op(x, 0)
+    got, want = op.meansd(), orc.meansd()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+    y = op.perform_op(x)
+    assert np.isfinite(y).all()
+    assert np.abs(y - y_ref).max() <= OP_RTOL * max(np.abs(y_ref).max(), 1.0)
+    v = rng.standard_normal(p)
+    assert np.abs(op.prod(v) - orc.prod(v)).max() <= OP_RTOL * max(np.abs(v).max() * p, 1.0)
+    assert np.abs(op.crossprod(x) - orc.crossprod(x)).max() <= OP_RTOL * n
+    op.close()
+
+
+def test_monomorphic_and_all_missing_columns(native_lib):
+    n, p = 37, 6
+    rng = np.random.default_rng(3)
+    codes = np.full((n, p), 3, dtype=np.uint8)
+    codes[:, 1] = 1
+    codes[:, 2:] = rng.choice([0, 2, 3, 1], size=(n, p - 2), p=[0.2, 0.3, 0.45, 0.05])
+    payload = _pack(codes)
+    op = _mk(payload, n, p)
+    orc = O.COracle(payload, n, p)
+    x = rng.standard_normal(n)
+    y_ref = orc.perform_op(x, 0)
+    y = op.perform_op(x)
+    assert np.isfinite(y).all() and np.allclose(y, y_ref, rtol=0, atol=1e-12)
+    t = op.crossprod(x)
+    assert t[0] == 0.0 and t[1] == 0.0     # sd <= VAR_TOL / NaN -> zero column (data.cpp:300)
+    assert abs(op.trace - orc.trace) <= 1e-12 * orc.trace
+
+
+def test_preloaded_meansd(native_lib):
+    """Data::use_preloaded_maf (data.cpp:293-297) with maf2meansd's sd
+    (randompca.cpp:745-751: 2p(1-p), no sqrt)."""
+    _, payload, n, p = load_fixture("data_chr1")
+    base = O.COracle(payload, n, p)
+    base.perform_op(np.ones(n), 0)
+    maf = base.meansd()[:, 0] / 2.0
+    pre = np.asfortranarray(np.stack([2 * maf, 2 * maf * (1 - maf)], axis=1))
+    op = _mk(payload, n, p, meansd=pre)
+    orc = O.COracle(payload, n, p, meansd=pre)
+    x = np.random.default_rng(9).standard_normal(n)
+    assert _relerr(op.perform_op(x), orc.perform_op(x, 0)) <= OP_RTOL
+    assert np.array_equal(op.meansd(), pre)
+
+
+def test_create_from_file_and_shards(native_lib):
+    from flashpca_b200 import Data, SVDWideOnline
+    stem = FIXTURES["data_chr1"]
+    d = Data()
+    d.read_pheno(stem + ".fam", 6)
+    d.geno_filename = stem + ".bed"
+    d.get_size()
+    d.prepare()
+    op = SVDWideOnline(d, 0, 3)
+    _, payload, n, p = load_fixture("data_chr1")
+    orc = O.COracle(payload, n, p)
+    x = np.random.default_rng(4).standard_normal(n)
+    y_ref = orc.perform_op(x, 0)
+    assert _relerr(op.perform_op(x), y_ref) <= OP_RTOL
+    assert np.array_equal(d.X_meansd, orc.meansd())
+    # two SNP shards sum to the whole (svdwide.cpp:48-59 distributed)
+    a = SVDWideOnline(d, 0, 3, snp_begin=0, snp_count=500)
+    b = SVDWideOnline(d, 0, 3, snp_begin=500, snp_count=0)
+    assert a.p + b.p == p
+    assert _relerr(a.perform_op(x) + b.perform_op(x), y_ref) <= OP_RTOL
+    assert abs(a.trace + b.trace - orc.trace) <= 1e-12 * orc.trace
+    assert np.array_equal(np.concatenate([a.meansd(), b.meansd()]), orc.meansd())
+
+
+def test_error_paths(native_lib):
+    from flashpca_b200 import Data, SVDWideOnline
+    from flashpca_b200._lib import FpbError
+    _, payload, n, p = load_fixture("data_chr1")
+    with pytest.raises(FpbError, match="unknown standardisation method: 1"):
+        _mk(payload, n, p, stand_method=1)      # data.cpp:283-288
+    d = Data()
+    d.N = 10
+    d.geno_filename = "/nonexistent/file.bed"
+    with pytest.raises(FpbError, match="Error reading file"):
+        SVDWideOnline(d, 0, 3)
+    op = _mk(payload, n, p)
+    with pytest.raises(FpbError, match="dimension mismatch"):
+        op.perform_op(np.zeros(n + 1))
+    with pytest.raises(FpbError, match="invalid nev/ncv"):
+        op.pca(10, 10, 5, 1e-6)
+
+
+def test_device_synth_matches_host_generator(native_lib):
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(1003, 300, seed=99, missing_rate=0.01)
+    op = s.create_operator()
+    got = op.bed_payload()
+    want = s.packed_bed()
+    assert np.array_equal(O.dense_codes(got, s.n, s.p), O.dense_codes(want, s.n, s.p))
+    sh = s.create_operator(j0=100, j1=250)
+    assert np.array_equal(O.dense_codes(sh.bed_payload(), s.n, 150),
+                          O.dense_codes(s.packed_bed(100, 250), s.n, 150))
+
+
+@pytest.mark.parametrize("name,ndim", [("data_chr1", 10), ("hapmap3", 10), ("hapmap3", 20)])
+def test_pca_vs_dense_eigh(native_lib, name, ndim):
+    """BASELINE config 0 (bundled HapMap3/data, --ndim 10) and the R-test fixture:
+    eigenvalues / pve within 1e-6 relative of dense eigh at the reference's
+    default tol 1e-6; eigenvectors and PCs within 1e-6 (sign-aligned) when the
+    solver is converged tighter (vector error ~ residual/gap)."""
+    from flashpca_b200 import Data, RandomPCA
+    stem = FIXTURES[name]
+    d = Data()
+    d.read_pheno(stem + ".fam", 6)
+    d.read_plink_fam(stem + ".fam")
+    d.geno_filename = stem + ".bed"
+    d.get_size()
+    d.prepare()
+    _, payload, n, p = load_fixture(name)
+    x, msd = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, ndim)
+    r = RandomPCA()
+    r.pca_fast(d, 0, ndim, 500, 1e-6, 1, do_loadings=True)
+    assert np.abs(r.d / ref["d"] - 1).max() < 1e-6
+    assert np.abs(r.pve / ref["pve"] - 1).max() < 1e-6
+    assert abs(r.trace / ref["trace"] - 1) < 1e-12
+    assert np.array_equal(r.X_meansd, msd)
+    assert 1 + 2 * ndim <= r.nops <= 500
+    r2 = RandomPCA()
+    r2.pca_fast(d, 0, ndim, 500, 1e-10, 1, do_loadings=True)
+    u = O.sign_align(r2.U, ref["U"])
+    assert np.abs(u - ref["U"]).max() < 1e-6
+    px = O.sign_align(r2.Px, ref["Px"])
+    assert np.abs(px - ref["Px"]).max() < 1e-6 * np.abs(ref["Px"]).max()
+    vref = O.dense_loadings(x, ref["U"], ref["d"], ref["div"])
+    v = O.sign_align(r2.V, vref)
+    assert np.abs(v - vref).max() < 1e-6 * np.abs(vref).max()
+    assert np.abs(np.linalg.norm(r2.U, axis=0) - 1).max() < 1e-12
+    # FID / IID ordering is the fam order, bit-exact
+    fid, iid = O.read_fam_ids(stem + ".fam")
+    assert d.fam_ids == fid and d.indiv_ids == iid
+    # --check semantics (randompca.cpp:663-703): mse < 1e-8 as README.md:207 expects
+    r2.check(d, 0, r2.U, r2.d)
+    assert r2.mse < 1e-8
+    # --project semantics (randompca.cpp:798-820): projecting the training data
+    # with its own loadings and mean/sd reproduces the PCs (test_project.R:23-26)
+    d.X_meansd = r2.X_meansd
+    d.use_preloaded_maf = True
+    r3 = RandomPCA()
+    r3.project(d, 0, r2.V)
+    assert np.abs(r3.Px - r2.Px).max() < 1e-5 * np.abs(r2.Px).max()
+
+
+def test_gpu_solver_vs_oracle_solver_same_tol(native_lib):
+    """Device IRLM and the oracle's Spectra restatement, same start vector and
+    tolerance, on the C oracle operator vs the CUDA operator."""
+    _, payload, n, p = load_fixture("data_chr1")
+    want = O.oracle_pca(payload, n, p, 10, tol=1e-6)
+    op = _mk(payload, n, p)
+    got = op.pca(10, 21, 500, 1e-6)
+    assert got["nconv"] == 10
+    assert np.abs(got["values"] / p / want["d"] - 1).max() < 1e-8
+    u = O.sign_align(got["vectors"], want["U"])
+    assert np.abs(u - want["U"]).max() < 5e-6
+    assert abs(int(got["nops"]) - int(want["nops"])) <= 25
+
+
+def test_dropin_boundary_with_external_solver(native_lib):
+    """The Spectra-shaped boundary: an external IRLM (the oracle's restatement
+    standing in for Spectra) drives perform_op(x_in, y_out) with host buffers."""
+    _, payload, n, p = load_fixture("data_chr1")
+    op = _mk(payload, n, p)
+    ybuf = np.zeros(n)
+
+    def cb(x):
+        op.perform_op(x, ybuf)
+        return ybuf.copy()
+
+    res = O.spectra_irlm(cb, n, 10, 21, 500, 1e-6)
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, 10)
+    assert res["nconv"] == 10
+    assert np.abs(res["values"] / p / ref["d"] - 1).max() < 1e-6
+
+
+def test_synthetic_structured_pca_vs_dense(native_lib):
+    """Synthetic Balding-Nichols matrix (the bench generator) at an oracle-sized
+    shape: k = 20 solve vs dense eigh."""
+    from flashpca_b200 import RandomPCA
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(1501, 6000, seed=5, npop=25, fst=0.05)
+    op = s.create_operator()
+    x, _ = O.dense_standardise(np.ascontiguousarray(s.codes().T))
+    ref = O.dense_pca(x, 20)
+    r = RandomPCA()
+    r.pca_fast(None, 0, 20, 500, 1e-6, op=op)
+    assert np.abs(r.d / ref["d"] - 1).max() < 1e-6
+    r.pca_fast(None, 0, 20, 500, 1e-11, op=op)
+    u = O.sign_align(r.U, ref["U"])
+    assert np.abs(u - ref["U"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("n,p", [(10000, 100000), (500000, 100000)])
+def test_full_size_properties(native_lib, n, p):
+    """BASELINE configs 1 and 2 at full size, through size-independent
+    properties of y = X X' x: linearity, symmetry, positive semi-definiteness,
+    consistency of the fused op with its two halves, and the trace identity
+    E[z' A z] = trace for Rademacher z (checked loosely)."""
+    import torch
+    if n * p > 2e10 and torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs > 60 GB HBM")
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(n, p, seed=20240601 + (1 if n == 10000 else 2))
+    op = s.create_operator()
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n)
+    z = rng.standard_normal(n)
+    ax, az = op.perform_op(x), op.perform_op(z)
+    scale = np.abs(ax).max()
+    # linearity: A(2x - 3z) = 2Ax - 3Az
+    lin = op.perform_op(2 * x - 3 * z)
+    assert np.abs(lin - (2 * ax - 3 * az)).max() <= 1e-11 * scale
+    # symmetry: z'Ax = x'Az
+    assert abs(z @ ax - x @ az) <= 1e-11 * abs(x @ ax)
+    # PSD and consistency with the halves: x'Ax = |X'x|^2, Ax = X (X'x)
+    t = op.crossprod(x)
+    assert abs(x @ ax - t @ t) <= 1e-11 * (t @ t)
+    assert np.abs(op.prod(t) - ax).max() <= 1e-11 * scale
+    # a slice of SNPs against the oracle (first 64 SNPs of the same generator)
+    sub = s.create_operator(j0=0, j1=64)
+    orc = O.COracle(s.packed_bed(0, 64), n, 64)
+    assert _relerr(sub.perform_op(x), orc.perform_op(x, 0)) <= OP_RTOL
+    assert np.array_equal(sub.meansd(), orc.meansd())
+    assert np.array_equal(op.meansd()[:64], orc.meansd())
+    # trace: every non-monomorphic SNP contributes about its non-missing count * var ratio
+    assert 0.5 * n * p < op.trace < 1.5 * n * p
