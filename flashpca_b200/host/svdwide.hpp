@@ -1,0 +1,116 @@
+// svdwide.hpp -- drop-in for upstream class SVDWideOnline (svdwide.h:32-107):
+// the matrix-free operator that flashpca passes to Spectra::SymEigsSolver
+// (randompca.cpp:173-175).  Same public surface -- rows(), cols(),
+// perform_op(const double*, double*), the block variants and `trace` -- with
+// every body forwarding to the C ABI in include/flashpca_b200.h.  The genotype
+// matrix is staged into HBM once, in the constructor; block_size is accepted
+// and ignored (there is no host-side N x block buffer any more).
+//
+// Errors surface as std::runtime_error, as upstream's Data I/O does
+// (data.cpp:160,188,287).
+#pragma once
+#include <stdexcept>
+#include <string>
+
+#include "data.hpp"
+#include "flashpca_b200.h"
+#include "matrix.hpp"
+
+namespace flashpca {
+
+class SVDWideOnline {
+ public:
+  double trace = 0;  // svdwide.h:37 (known right after staging)
+
+  SVDWideOnline(Data& dat_, unsigned int block_size_, int stand_method_, bool verbose_,
+                int device = 0)
+      : dat(dat_), n(dat_.N), p(dat_.nsnps) {
+    verbose = verbose_;
+    block_size = block_size_;
+    stand_method = stand_method_;
+    nops = 1;
+    const double* pre = dat.use_preloaded_maf ? dat.X_meansd.data() : nullptr;
+    if (dat.use_preloaded_maf && dat.X_meansd.rows() != dat.nsnps)
+      throw std::runtime_error("preloaded mean/sd table does not match the number of SNPs");
+    // the standardisation method is Data's, as in data.cpp:279-288
+    if (fpb_create_from_file(&h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps,
+                             dat.stand_method_x, pre, device))
+      throw std::runtime_error(fpb_last_error(nullptr));
+    fpb_get_trace(h, &trace);
+    if (!dat.use_preloaded_maf) {
+      dat.X_meansd = Matrix(p, 2);
+      check(fpb_get_meansd(h, dat.X_meansd.data()));
+    }
+  }
+  ~SVDWideOnline() { fpb_destroy(h); }
+  SVDWideOnline(const SVDWideOnline&) = delete;
+  SVDWideOnline& operator=(const SVDWideOnline&) = delete;
+
+  inline unsigned int rows() const { return n; }
+  inline unsigned int cols() const { return n; }
+
+  // y = X X' x (svdwide.cpp:21-68)
+  void perform_op(const double* x_in, double* y_out) {
+    check(fpb_perform_op(h, x_in, y_out));
+    nops++;
+  }
+  // Y = X X' M (svdwide.cpp:71-118, 229-275)
+  Matrix perform_op_mat(const Matrix& x) {
+    need_rows(x, n);
+    Matrix Y(n, x.cols());
+    check(fpb_perform_op_multi(h, x.data(), (uint32_t)x.cols(), Y.data()));
+    nops++;
+    return Y;
+  }
+  Matrix perform_op_multi(const Matrix& x) { return perform_op_mat(x); }
+  // y = X' x (svdwide.cpp:122-153)
+  void crossprod(double* x_in, double* y_out) {
+    check(fpb_crossprod(h, x_in, y_out));
+    nops++;
+  }
+  Matrix crossprod2(const Matrix& x) {  // svdwide.cpp:157-188
+    need_rows(x, n);
+    Matrix Y(p, x.cols());
+    check(fpb_crossprod_multi(h, x.data(), (uint32_t)x.cols(), Y.data()));
+    nops++;
+    return Y;
+  }
+  // y = X x (svdwide.cpp:193-226)
+  void prod(double* x_in, double* y_out) {
+    check(fpb_prod(h, x_in, y_out));
+    nops++;
+  }
+  Matrix prod3(const Matrix& x) {  // svdwide.cpp:312-343
+    need_rows(x, p);
+    Matrix Y(n, x.cols());
+    check(fpb_prod_multi(h, x.data(), (uint32_t)x.cols(), Y.data()));
+    nops++;
+    return Y;
+  }
+  Matrix prod2(const Matrix& x) {  // svdwide.cpp:278-309: Y = x' X
+    Matrix T = crossprod2(x);
+    Matrix Y(x.cols(), p);
+    for (size_t c = 0; c < x.cols(); c++)
+      for (size_t j = 0; j < p; j++) Y(c, j) = T(j, c);
+    return Y;
+  }
+
+  fpb_handle* handle() { return h; }
+
+ private:
+  void check(int rc) {
+    if (rc) throw std::runtime_error(fpb_last_error(h));
+  }
+  static void need_rows(const Matrix& m, size_t r) {
+    if (m.rows() != r) throw std::runtime_error("operator argument has the wrong number of rows");
+  }
+  Data& dat;
+  const unsigned int n, p;
+  int stand_method;
+  bool verbose;
+  unsigned int nops;
+  unsigned int block_size;
+  fpb_handle* h = nullptr;
+};
+
+}  // namespace flashpca
