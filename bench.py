@@ -288,13 +288,14 @@ def run_b200(a):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "kernel": "perform_op = k_crossprod + k_prod (two passes over the staged bed)",
+        "kernel": "perform_op = k_imma_gemv over the SNP-major copy (X'x) + k_imma_gemv over the "
+                  "individual-major copy (X t); each pass reads ceil(N/4)*P packed bytes",
         "algorithmic_bytes_per_launch": alg_bytes / world,
         "kernels": [
-            {"name": "k_crossprod", "ms": k_ms[0], "algorithmic_bytes": kern_bytes,
+            {"name": "crossprod pass (slice + k_imma_gemv[SNP-major] + finalize)", "ms": k_ms[0], "algorithmic_bytes": kern_bytes,
              "achieved": kern_bytes / (k_ms[0] * 1e-3) / 1e9,
              "frac": kern_bytes / (k_ms[0] * 1e-3) / 1e9 / peak},
-            {"name": "k_prod", "ms": k_ms[1], "algorithmic_bytes": kern_bytes,
+            {"name": "prod pass (slice + k_imma_gemv[individual-major] + finalize)", "ms": k_ms[1], "algorithmic_bytes": kern_bytes,
              "achieved": kern_bytes / (k_ms[1] * 1e-3) / 1e9,
              "frac": kern_bytes / (k_ms[1] * 1e-3) / 1e9 / peak},
         ],

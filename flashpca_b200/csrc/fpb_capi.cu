@@ -1,10 +1,15 @@
 // fpb_capi.cu -- C ABI (include/flashpca_b200.h) over the sm_100a kernels.
 //
 // Host-side state of one staged genotype matrix (or SNP shard of one):
-//   d_bed    nsnps x pitch bytes   staged 2-bit genotypes (see fpb_kernels.cuh)
-//   d_lut    nsnps x double4       per-SNP code -> standardised value table
-//   d_meansd nsnps x 2             Data::X_meansd (data.cpp:290-291)
-//   d_t, d_coef                    per-op scratch (X'x and the prod coefficients)
+//   d_gs     nsnps x pitch_s bytes  SNP-major 2-bit dosage codes (fpb_kernels.cuh)
+//   d_gi     N x pitch_i bytes      individual-major copy (tensor path only)
+//   d_scale  nsnps x (mean, 1/sd)   d_lut  nsnps x double4 (generic path table)
+//   d_meansd nsnps x 2              Data::X_meansd (data.cpp:290-291)
+//   CSR lists of the missing genotypes by SNP and by individual (tensor path)
+//   per-op scratch: digit slices, split partials, a/b/corr vectors
+// Two compute paths share the staged data: the tensor path (fpb_imma.cuh, used
+// when the missing rate is <= 3 %) and the generic FP64 path (fpb_kernels.cuh).
+// FPB_PATH=generic|imma in the environment forces one (tests exercise both).
 // No CPU fallback exists: if CUDA is unusable every entry point fails.
 #include "../../include/flashpca_b200.h"
 
@@ -18,6 +23,9 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
+
+#include "fpb_imma.cuh"
 #include "fpb_irlm.cuh"
 #include "fpb_kernels.cuh"
 
@@ -73,20 +81,40 @@ constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 struct fpb_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
-  uint64_t n = 0, nsnps = 0, np = 0, pitch = 0;
+  cudaStream_t side = nullptr;            // CSR gathers, overlapped with the contraction
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  uint64_t n = 0, nsnps = 0, np = 0;
+  uint64_t pitch_s = 0, pitch_i = 0;
   int stand_method = 0;
   int sm_count = 148;
-  uint8_t* d_bed = nullptr;
+  uint8_t* d_gs = nullptr;
+  uint8_t* d_gi = nullptr;
   double4* d_lut = nullptr;
+  double2* d_scale = nullptr;
   double* d_meansd = nullptr;
+  // generic path scratch
   double* d_t = nullptr;
   double4* d_coef = nullptr;
   double* d_c0 = nullptr;
-  double* d_in = nullptr;   // host-pointer API staging (grown on demand)
+  Tiling tl;
+  // tensor path
+  bool use_imma = false;
+  uint64_t nmissing = 0;
+  uint64_t *d_rowptr_s = nullptr, *d_rowptr_i = nullptr;
+  uint32_t *d_col_s = nullptr, *d_col_i = nullptr;
+  uint4* d_slices = nullptr;
+  double* d_part = nullptr;
+  double *d_a = nullptr, *d_b = nullptr, *d_corr = nullptr;
+  double *d_pmax = nullptr, *d_psum = nullptr;
+  double *d_mx = nullptr, *d_mc = nullptr;  // per-SNP / per-individual missing-genotype sums
+  fpb::VecScale* d_sc = nullptr;  // [0] = x, [1] = a, [2] = b
+  uint32_t nchunks_s = 0, nchunks_i = 0, splits_s = 1, splits_i = 1, cps_s = 1, cps_i = 1;
+  uint64_t part_stride = 0;
+  // host-pointer API staging (grown on demand)
+  double* d_in = nullptr;
   double* d_out = nullptr;
   size_t in_cap = 0, out_cap = 0;
   double trace = 0.0;
-  Tiling tl;
   NcclComm comm = nullptr;
   int nranks = 1, rank = 0;
   uint64_t launches = 0;
@@ -137,9 +165,12 @@ Tiling pick_tiling(uint64_t words_per_row, uint64_t nsnps, int sm_count) {
   return t;
 }
 
+constexpr int kWarps = 8;           // warps per CTA of k_imma_gemv (128 rows)
+constexpr uint32_t kVecBlocks = 256;  // blocks of the vector max/sum reduction
+
 int alloc_common(fpb_handle* h, uint64_t n, uint64_t nsnps, int stand_method, int device) {
   if (n == 0 || nsnps == 0) FPB_FAIL(h, "empty genotype matrix (N == 0 or nsnps == 0)");
-  if (nsnps > 0xFFFFFFF0ull) FPB_FAIL(h, "too many SNPs for one handle");
+  if (nsnps > 0xFFFFFFF0ull || n > 0xFFFFFFF0ull) FPB_FAIL(h, "matrix too large for one handle");
   if (stand_method != FPB_STANDARDISE_BINOM && stand_method != FPB_STANDARDISE_BINOM2)
     FPB_FAIL(h, std::string("unknown standardisation method: ") + std::to_string(stand_method));
   int ndev = 0;
@@ -154,45 +185,151 @@ int alloc_common(fpb_handle* h, uint64_t n, uint64_t nsnps, int stand_method, in
   FPB_CUDA(h, cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
   FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->n = n;
   h->nsnps = nsnps;
   h->np = (n + 3) / 4;
-  h->pitch = (h->np + 15) / 16 * 16;
+  h->pitch_s = (h->np + 63) / 64 * 64;
+  h->pitch_i = ((nsnps + 3) / 4 + 63) / 64 * 64;
   h->stand_method = stand_method;
-  FPB_CUDA(h, cudaMalloc(&h->d_bed, h->pitch * nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_gs, h->pitch_s * nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_lut, sizeof(double4) * nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_scale, sizeof(double2) * nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_meansd, sizeof(double) * 2 * nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_t, sizeof(double) * nsnps));
-  FPB_CUDA(h, cudaMalloc(&h->d_coef, sizeof(double4) * nsnps));
-  FPB_CUDA(h, cudaMalloc(&h->d_c0, sizeof(double)));
-  h->tl = pick_tiling(h->pitch / 4, nsnps, h->sm_count);
+  h->tl = pick_tiling(h->pitch_s / 4, nsnps, h->sm_count);
   return 0;
 }
 
-// padding fix-up + first-visit statistics (data.cpp:257-322) + trace
+// exclusive scan of per-row counts on the host -> device rowptr (rows + 1)
+int build_rowptr(fpb_handle* h, const uint32_t* d_counts, uint64_t rows, uint64_t** d_rowptr,
+                 uint64_t* total) {
+  std::vector<uint32_t> cnt(rows);
+  FPB_CUDA(h, cudaMemcpyAsync(cnt.data(), d_counts, sizeof(uint32_t) * rows,
+                              cudaMemcpyDeviceToHost, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<uint64_t> ptr(rows + 1);
+  uint64_t acc = 0;
+  for (uint64_t r = 0; r < rows; r++) {
+    ptr[r] = acc;
+    acc += cnt[r];
+  }
+  ptr[rows] = acc;
+  *total = acc;
+  FPB_CUDA(h, cudaMalloc(d_rowptr, sizeof(uint64_t) * (rows + 1)));
+  FPB_CUDA(h, cudaMemcpyAsync(*d_rowptr, ptr.data(), sizeof(uint64_t) * (rows + 1),
+                              cudaMemcpyHostToDevice, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// Column splits of the contraction grid: enough CTAs for >= ~20 waves (2 CTAs
+// per SM resident) so the last partial wave costs little, but >= 16 chunks per
+// split so the pipeline prologue stays amortised.
+void pick_splits(uint32_t rows, uint32_t nchunks, int sm_count, uint32_t* splits, uint32_t* cps) {
+  uint32_t tiles = (rows + 16 * kWarps - 1) / (16 * kWarps);
+  uint32_t want = (40u * sm_count + tiles - 1) / tiles;
+  uint32_t s = std::min<uint32_t>(want, std::max<uint32_t>(1, nchunks / 16));
+  s = std::max<uint32_t>(1, std::min<uint32_t>(s, 64));
+  *cps = (nchunks + s - 1) / s;
+  *splits = (nchunks + *cps - 1) / *cps;
+}
+
+// raw bed bytes are in d_gs (pitch_s): recode, statistics (data.cpp:257-322),
+// trace, and -- when the missing rate allows -- the tensor path's second copy
+// and CSR lists.
 int finish_create(fpb_handle* h, const double* preloaded_meansd) {
-  uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
-  fpb::k_fix_padding<<<gb, 256, 0, h->stream>>>(h->d_bed, h->nsnps, h->n, h->pitch);
+  uint64_t nwords = h->nsnps * (h->pitch_s / 4);
+  fpb::k_recode_rows<<<(uint32_t)((nwords + 255) / 256), 256, 0, h->stream>>>(h->d_gs, h->nsnps,
+                                                                              h->n, h->pitch_s);
   h->launches++;
   if (preloaded_meansd)
     FPB_CUDA(h, cudaMemcpyAsync(h->d_meansd, preloaded_meansd, sizeof(double) * 2 * h->nsnps,
                                 cudaMemcpyHostToDevice, h->stream));
   double* d_tracej = nullptr;
+  uint32_t* d_cnt = nullptr;
   FPB_CUDA(h, cudaMalloc(&d_tracej, sizeof(double) * h->nsnps));
+  FPB_CUDA(h, cudaMalloc(&d_cnt, sizeof(uint32_t) * std::max(h->nsnps, h->n)));
   uint32_t gs = (uint32_t)((h->nsnps * 32 + 255) / 256);
-  fpb::k_snp_stats<<<gs, 256, 0, h->stream>>>(h->d_bed, h->nsnps, h->pitch, h->stand_method,
-                                              preloaded_meansd != nullptr, h->d_meansd, h->d_lut,
-                                              d_tracej);
+  fpb::k_snp_stats<<<gs, 256, 0, h->stream>>>(h->d_gs, h->nsnps, h->n, h->pitch_s,
+                                              h->stand_method, preloaded_meansd != nullptr,
+                                              h->d_meansd, h->d_lut, h->d_scale, d_tracej, d_cnt);
   h->launches++;
   std::vector<double> tr(h->nsnps);
   FPB_CUDA(h, cudaMemcpyAsync(tr.data(), d_tracej, sizeof(double) * h->nsnps,
                               cudaMemcpyDeviceToHost, h->stream));
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  FPB_CUDA(h, cudaFree(d_tracej));
   FPB_CUDA(h, cudaGetLastError());
   double s = 0.0;
   for (double v : tr) s += v;  // SNP order, like the block loop of svdwide.cpp:44-61
   h->trace = s;
+  cudaFree(d_tracej);
+
+  if (build_rowptr(h, d_cnt, h->nsnps, &h->d_rowptr_s, &h->nmissing)) return 1;
+  const char* force = getenv("FPB_PATH");
+  h->use_imma = (double)h->nmissing <= 0.03 * (double)h->n * (double)h->nsnps;
+  if (force && !strcmp(force, "generic")) h->use_imma = false;
+  if (force && !strcmp(force, "imma")) h->use_imma = true;
+
+  if (!h->use_imma) {
+    cudaFree(h->d_rowptr_s);
+    h->d_rowptr_s = nullptr;
+    cudaFree(d_cnt);
+    FPB_CUDA(h, cudaMalloc(&h->d_coef, sizeof(double4) * h->nsnps));
+    FPB_CUDA(h, cudaMalloc(&h->d_c0, sizeof(double)));
+    return 0;
+  }
+
+  // ---- tensor path staging: transposed copy, CSR lists, scratch
+  FPB_CUDA(h, cudaMalloc(&h->d_gi, h->pitch_i * h->n));
+  FPB_CUDA(h, cudaMemsetAsync(h->d_gi, 0, h->pitch_i * h->n, h->stream));
+  {
+    dim3 grid((uint32_t)((h->n + 127) / 128), (uint32_t)((h->nsnps + 127) / 128));
+    fpb::k_transpose_2bit<<<grid, 256, 0, h->stream>>>(h->d_gs, h->nsnps, h->pitch_s, h->d_gi,
+                                                       h->n, h->pitch_i);
+    h->launches++;
+  }
+  if (h->nmissing) {
+    FPB_CUDA(h, cudaMalloc(&h->d_col_s, sizeof(uint32_t) * h->nmissing));
+    FPB_CUDA(h, cudaMalloc(&h->d_col_i, sizeof(uint32_t) * h->nmissing));
+    fpb::k_fill_missing_csr<<<gs, 256, 0, h->stream>>>(h->d_gs, h->nsnps, h->pitch_s,
+                                                       h->d_rowptr_s, h->d_col_s);
+    uint32_t gi = (uint32_t)((h->n * 32 + 255) / 256);
+    fpb::k_row_missing<<<gi, 256, 0, h->stream>>>(h->d_gi, h->n, h->pitch_i, d_cnt);
+    uint64_t total_i = 0;
+    if (build_rowptr(h, d_cnt, h->n, &h->d_rowptr_i, &total_i)) return 1;
+    if (total_i != h->nmissing) FPB_FAIL(h, "internal error: transposed copy disagrees on missing count");
+    fpb::k_fill_missing_csr<<<gi, 256, 0, h->stream>>>(h->d_gi, h->n, h->pitch_i, h->d_rowptr_i,
+                                                       h->d_col_i);
+    h->launches += 3;
+  } else {
+    cudaFree(h->d_rowptr_s);
+    h->d_rowptr_s = nullptr;
+  }
+  cudaFree(d_cnt);
+  h->nchunks_s = (uint32_t)((h->pitch_s + fpb::kChunkBytes - 1) / fpb::kChunkBytes);
+  h->nchunks_i = (uint32_t)((h->pitch_i + fpb::kChunkBytes - 1) / fpb::kChunkBytes);
+  pick_splits((uint32_t)h->nsnps, h->nchunks_s, h->sm_count, &h->splits_s, &h->cps_s);
+  pick_splits((uint32_t)h->n, h->nchunks_i, h->sm_count, &h->splits_i, &h->cps_i);
+  h->part_stride = std::max(h->n, h->nsnps);
+  uint64_t max_chunks = std::max(h->nchunks_s, h->nchunks_i);
+  FPB_CUDA(h, cudaMalloc(&h->d_slices, sizeof(uint4) * max_chunks * fpb::kChunkWords * 8));
+  FPB_CUDA(h, cudaMalloc(&h->d_part, sizeof(double) * h->part_stride *
+                                         std::max(h->splits_s, h->splits_i)));
+  FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * h->nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_b, sizeof(double) * h->nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * h->nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->d_pmax, sizeof(double) * kVecBlocks));
+  FPB_CUDA(h, cudaMalloc(&h->d_psum, sizeof(double) * kVecBlocks));
+  FPB_CUDA(h, cudaMalloc(&h->d_sc, sizeof(fpb::VecScale) * 3));
+  if (h->nmissing) {
+    FPB_CUDA(h, cudaMalloc(&h->d_mx, sizeof(double) * h->nsnps));
+    FPB_CUDA(h, cudaMalloc(&h->d_mc, sizeof(double) * h->n));
+  }
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  FPB_CUDA(h, cudaGetLastError());
   return 0;
 }
 
@@ -212,24 +349,24 @@ int ensure_staging(fpb_handle* h, size_t in_elems, size_t out_elems) {
   return 0;
 }
 
-// t (nsnps) = X' x
-void launch_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
+// ------------------------------ generic FP64 path --------------------------
+
+void generic_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
   const Tiling& t = h->tl;
   cudaMemsetAsync(d_t, 0, sizeof(double) * h->nsnps, h->stream);
   dim3 grid(t.chunks, t.splits);
   if (t.W == 1)
-    fpb::k_crossprod<1><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n,
+    fpb::k_crossprod<1><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
                                                           (uint32_t)h->nsnps, t.snps_per_split,
                                                           d_x, h->d_lut, d_t);
   else
-    fpb::k_crossprod<2><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n,
+    fpb::k_crossprod<2><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
                                                           (uint32_t)h->nsnps, t.snps_per_split,
                                                           d_x, h->d_lut, d_t);
   h->launches++;
 }
 
-// y (N) = X v
-void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
+void generic_prod(fpb_handle* h, const double* d_v, double* d_y) {
   const Tiling& t = h->tl;
   uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
   fpb::k_prod_coef<<<gb, 256, 0, h->stream>>>(h->d_lut, d_v, (uint32_t)h->nsnps, h->d_coef);
@@ -237,12 +374,108 @@ void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
   if (t.splits > 1) cudaMemsetAsync(d_y, 0, sizeof(double) * h->n, h->stream);
   dim3 grid(t.chunks, t.splits);
   if (t.W == 1)
-    fpb::k_prod<1><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n, (uint32_t)h->nsnps,
-                                                     t.snps_per_split, h->d_coef, h->d_c0, d_y);
+    fpb::k_prod<1><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
+                                                     (uint32_t)h->nsnps, t.snps_per_split,
+                                                     h->d_coef, h->d_c0, d_y);
   else
-    fpb::k_prod<2><<<grid, t.block, 0, h->stream>>>(h->d_bed, h->pitch, h->n, (uint32_t)h->nsnps,
-                                                     t.snps_per_split, h->d_coef, h->d_c0, d_y);
+    fpb::k_prod<2><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
+                                                     (uint32_t)h->nsnps, t.snps_per_split,
+                                                     h->d_coef, h->d_c0, d_y);
   h->launches += 3;
+}
+
+// ------------------------------ tensor path --------------------------------
+
+void vec_prepare(fpb_handle* h, const double* d_v, uint64_t len, int slot) {
+  fpb::k_vec_partial<<<kVecBlocks, 256, 0, h->stream>>>(d_v, len, h->d_pmax, h->d_psum);
+  fpb::k_vec_final<<<1, 32, 0, h->stream>>>(h->d_pmax, h->d_psum, kVecBlocks, h->d_sc + slot);
+  h->launches += 2;
+}
+
+// part[split][row] = sum_s 128^s sum_col G[row][col] * digit_s(v[col])
+void imma_contract(fpb_handle* h, const uint8_t* G, uint64_t pitch, uint32_t rows,
+                   const double* d_v, uint64_t vlen, int slot, uint32_t nchunks, uint32_t splits,
+                   uint32_t cps) {
+  uint32_t nwq = nchunks * fpb::kChunkWords;
+  fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(d_v, vlen, nwq, h->d_sc + slot,
+                                                             h->d_slices);
+  dim3 grid((rows + 16 * kWarps - 1) / (16 * kWarps), splits);
+  fpb::k_imma_gemv<kWarps><<<grid, kWarps * 32, 0, h->stream>>>(G, pitch, rows, h->d_slices,
+                                                                nchunks, cps, h->d_part,
+                                                                h->part_stride);
+  h->launches += 2;
+}
+
+// out[r] = sum of coef over the missing entries of row r, on the side stream
+// (forked after everything already enqueued on the main stream)
+void fork_gather(fpb_handle* h, const uint64_t* rowptr, const uint32_t* colidx,
+                 const double* coef, uint64_t nrows, double* out) {
+  cudaEventRecord(h->ev_fork, h->stream);
+  cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+  uint32_t gb = (uint32_t)((nrows * 32 + 255) / 256);
+  fpb::k_csr_gather<<<gb, 256, 0, h->side>>>(rowptr, colidx, coef, nrows, out);
+  cudaEventRecord(h->ev_join, h->side);
+  h->launches++;
+}
+void join_gather(fpb_handle* h) { cudaStreamWaitEvent(h->stream, h->ev_join, 0); }
+
+// first half: t = X'x (d_t) and/or the a, b, corr inputs of the second half
+void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_half) {
+  if (h->nmissing) fork_gather(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
+  vec_prepare(h, d_x, h->n, 0);
+  imma_contract(h, h->d_gs, h->pitch_s, (uint32_t)h->nsnps, d_x, h->n, 0, h->nchunks_s,
+                h->splits_s, h->cps_s);
+  if (h->nmissing) join_gather(h);
+  uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
+  fpb::k_finalize_crossprod<<<gb, 256, 0, h->stream>>>(
+      h->d_part, h->splits_s, h->part_stride, (uint32_t)h->nsnps, h->d_sc + 0, h->d_scale,
+      h->nmissing ? h->d_mx : nullptr, d_t, second_half ? h->d_a : nullptr, h->d_b, h->d_corr);
+  h->launches++;
+}
+
+// second half from a, b, corr already in the handle: y = F - Sb + missing terms
+void imma_prod_tail(fpb_handle* h, double* d_y) {
+  if (h->nmissing) fork_gather(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
+  vec_prepare(h, h->d_a, h->nsnps, 1);
+  vec_prepare(h, h->d_b, h->nsnps, 2);
+  imma_contract(h, h->d_gi, h->pitch_i, (uint32_t)h->n, h->d_a, h->nsnps, 1, h->nchunks_i,
+                h->splits_i, h->cps_i);
+  if (h->nmissing) join_gather(h);
+  uint32_t gb = (uint32_t)((h->n + 255) / 256);
+  fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, h->splits_i, h->part_stride, h->n,
+                                                  h->d_sc + 1, h->d_sc + 2,
+                                                  h->nmissing ? h->d_mc : nullptr, d_y);
+  h->launches++;
+}
+
+// t (nsnps) = X' x
+void launch_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
+  if (h->use_imma) imma_crossprod(h, d_x, d_t, false);
+  else generic_crossprod(h, d_x, d_t);
+}
+
+// y (N) = X v
+void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
+  if (h->use_imma) {
+    uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
+    fpb::k_prod_inputs<<<gb, 256, 0, h->stream>>>(d_v, h->d_scale, (uint32_t)h->nsnps, h->d_a,
+                                                  h->d_b, h->d_corr);
+    h->launches++;
+    imma_prod_tail(h, d_y);
+  } else {
+    generic_prod(h, d_v, d_y);
+  }
+}
+
+// y (N) = X X' x
+void launch_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
+  if (h->use_imma) {
+    imma_crossprod(h, d_x, nullptr, true);
+    imma_prod_tail(h, d_y);
+  } else {
+    generic_crossprod(h, d_x, h->d_t);
+    generic_prod(h, h->d_t, d_y);
+  }
 }
 
 int allreduce(fpb_handle* h, double* d_buf, size_t count) {
@@ -274,7 +507,7 @@ int fpb_create(fpb_handle** out, const unsigned char* bed_payload, uint64_t n, u
   fpb_handle* h = new fpb_handle();
   if (alloc_common(h, n, nsnps, stand_method, device) ||
       [&]() -> int {
-        FPB_CUDA(h, cudaMemcpy2DAsync(h->d_bed, h->pitch, bed_payload, h->np, h->np, nsnps,
+        FPB_CUDA(h, cudaMemcpy2DAsync(h->d_gs, h->pitch_s, bed_payload, h->np, h->np, nsnps,
                                       cudaMemcpyHostToDevice, h->stream));
         return 0;
       }() ||
@@ -328,7 +561,7 @@ int fpb_create_from_file(fpb_handle** out, const char* bed_path, uint64_t n, uin
           failed = 1;
           break;
         }
-        if (cudaMemcpy2DAsync(h->d_bed + r * h->pitch, h->pitch, pin[b], np, np, rows,
+        if (cudaMemcpy2DAsync(h->d_gs + r * h->pitch_s, h->pitch_s, pin[b], np, np, rows,
                               cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
           h->err = "CUDA error staging bed";
           failed = 1;
@@ -376,7 +609,7 @@ int fpb_create_synthetic(fpb_handle** out, uint64_t n, uint64_t nsnps, uint64_t 
       uint64_t blocks = (total + 255) / 256;
       if (blocks > 0x7FFFFFFFull) FPB_FAIL(h, "synthetic matrix too large for one launch");
       fpb::k_synth_bed<<<(uint32_t)blocks, 256, 0, h->stream>>>(
-          h->d_bed, nsnps, n, h->pitch, snp_offset, d_pop, d_thr, missing_threshold, seed);
+          h->d_gs, nsnps, n, h->pitch_s, snp_offset, d_pop, d_thr, missing_threshold, seed);
       h->launches++;
       FPB_CUDA(h, cudaStreamSynchronize(h->stream));
       cudaFree(d_pop);
@@ -398,8 +631,28 @@ void fpb_destroy(fpb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->side) cudaStreamSynchronize(h->side);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->d_bed);
+  cudaFree(h->d_gs);
+  cudaFree(h->d_gi);
+  cudaFree(h->d_scale);
+  cudaFree(h->d_rowptr_s);
+  cudaFree(h->d_rowptr_i);
+  cudaFree(h->d_col_s);
+  cudaFree(h->d_col_i);
+  cudaFree(h->d_slices);
+  cudaFree(h->d_part);
+  cudaFree(h->d_a);
+  cudaFree(h->d_b);
+  cudaFree(h->d_corr);
+  cudaFree(h->d_pmax);
+  cudaFree(h->d_psum);
+  cudaFree(h->d_sc);
+  cudaFree(h->d_mx);
+  cudaFree(h->d_mc);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   cudaFree(h->d_lut);
   cudaFree(h->d_meansd);
   cudaFree(h->d_t);
@@ -435,9 +688,15 @@ int fpb_get_trace(fpb_handle* h, double* out_trace) {
 int fpb_get_bed(fpb_handle* h, unsigned char* out_payload) {
   if (!h || !out_payload) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
-  FPB_CUDA(h, cudaMemcpy2DAsync(out_payload, h->np, h->d_bed, h->pitch, h->np, h->nsnps,
-                                cudaMemcpyDeviceToHost, h->stream));
+  uint8_t* d_tmp = nullptr;
+  uint64_t total = h->nsnps * h->np;
+  FPB_CUDA(h, cudaMalloc(&d_tmp, total));
+  fpb::k_decode_rows<<<(uint32_t)((total + 255) / 256), 256, 0, h->stream>>>(
+      h->d_gs, d_tmp, h->nsnps, h->np, h->pitch_s);
+  h->launches++;
+  FPB_CUDA(h, cudaMemcpyAsync(out_payload, d_tmp, total, cudaMemcpyDeviceToHost, h->stream));
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_tmp);
   return 0;
 }
 
@@ -470,10 +729,8 @@ int fpb_prod_multi_dev(fpb_handle* h, const double* d_v, uint32_t k, double* d_y
 int fpb_perform_op_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, double* d_y) {
   if (!h || !d_m || !d_y || k == 0) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
-  for (uint32_t c = 0; c < k; c++) {
-    launch_crossprod(h, d_m + (uint64_t)c * h->n, h->d_t);
-    launch_prod(h, h->d_t, d_y + (uint64_t)c * h->n);
-  }
+  for (uint32_t c = 0; c < k; c++)
+    launch_perform_op(h, d_m + (uint64_t)c * h->n, d_y + (uint64_t)c * h->n);
   if (check_launch(h)) return 1;
   return allreduce(h, d_y, (size_t)h->n * k);
 }

@@ -1,0 +1,386 @@
+// fpb_imma.cuh -- the tensor-core perform_op path: exact fixed-point
+// 2-bit x int8-slice contraction.
+//
+// Why not FP64 on the CUDA cores: B200 issues ~62 FP64 adds/clk/SM (measured,
+// profiles/r01_microbench_b200.txt); y = X X' x needs >= 2 of them per genotype,
+// which caps a CUDA-core kernel near 15 genotypes/clk/SM, while HBM delivers
+// ~100 genotypes/clk/SM of packed input.  The int8 tensor path (mma.sync
+// m16n8k32, measured 2035 MAC/clk/SM) contracts 512 genotypes x 8 slices per
+// instruction straight from registers, so the kernel becomes HBM-bound.
+//
+// Maths.  With dosage codes e_ij in {0,1,2,3=missing} (fpb_kernels.cuh),
+// Mx_j = sum of x_i over the missing genotypes of SNP j, Sx = sum_i x_i:
+//   E_j  = sum_i e_ij x_i                                   (tensor cores, exact)
+//   t_j  = (X'x)_j = [ (E_j - 3 Mx_j) - mu_j (Sx - Mx_j) ] / sd_j
+// and for y = X v with a_j = v_j / sd_j, b_j = mu_j a_j, Sb = sum_j b_j:
+//   F_i  = sum_j e_ij a_j                                   (tensor cores, exact)
+//   y_i  = F_i - Sb + sum_{j missing for i} (b_j - 3 a_j)
+// The missing-genotype terms come from two CSR index lists built at staging
+// (missing rate is ~0.15 % in real data; above ~3 % the generic FP64 path is
+// used instead).
+//
+// Exactness.  The input vector is converted to fixed point with a power-of-two
+// step delta = 2^(ex-54), ex = exponent of max|x|: Q_i = rint(x_i / (4^f delta))
+// where f = (column & 3) is the position of the genotype inside its byte, and
+// Q_i is cut into 8 balanced base-128 digits (int8).  The A operand is the packed
+// word ANDed with 0x03 / 0x0C / 0x30 / 0xC0 byte masks -- one LOP3 per 4
+// genotypes, no shifts: field f then carries e * 4^f, which the 4^-f in Q_i
+// undoes.  Products and int32 accumulation are exact; slices are recombined in
+// FP64 (sum_s 128^s D_s, every term exact).  The only rounding is the input
+// quantisation, <= 2^-48 max|x| per element.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "fpb_kernels.cuh"
+
+namespace fpb {
+
+constexpr int kSliceBits = 54;   // |Q| < 2^54
+constexpr int kChunkBytes = 512; // packed bytes of one row per pipeline chunk (2048 columns)
+constexpr int kChunkWords = kChunkBytes / 4;     // 128 word-columns
+constexpr int kFlushChunks = 32;                 // int32 accumulators -> FP64 every 65536 columns
+
+struct VecScale {   // written by k_vec_prepare, read by slicing / finalize kernels
+  double sum;       // sum of the vector (deterministic order)
+  double delta;     // fixed-point step 2^(ex - 54), 0 for an all-zero vector, NaN if non-finite
+  double inv_delta_unused;
+  int ex;
+  int pad;
+};
+
+// ---------------------------------------------------------------------------
+// Vector preparation: max|v| and sum(v) with a fixed-order two-stage reduction.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_vec_partial(const double* __restrict__ v, uint64_t n, double* __restrict__ pmax,
+              double* __restrict__ psum) {
+  __shared__ double smax[8], ssum[8];
+  uint64_t per = (n + gridDim.x - 1) / gridDim.x;
+  uint64_t b = blockIdx.x * per, e = min(n, b + per);
+  double m = 0.0, s = 0.0;
+  for (uint64_t i = b + threadIdx.x; i < e; i += 256) {
+    double a = v[i];
+    s += a;
+    a = fabs(a);
+    m = (a > m || a != a) ? a : m;  // NaN propagates
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double om = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (om > m || om != om) ? om : m;
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smax[threadIdx.x >> 5] = m;
+    ssum[threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) {
+      m = (smax[w] > m || smax[w] != smax[w]) ? smax[w] : m;
+      s += ssum[w];
+    }
+    // thread 0 holds warp 0's values in m, s
+    pmax[blockIdx.x] = m;
+    psum[blockIdx.x] = s;
+  }
+}
+
+__global__ void k_vec_final(const double* __restrict__ pmax, const double* __restrict__ psum,
+                            uint32_t nblocks, VecScale* __restrict__ out) {
+  // one warp; lane l combines blocks l, l+32, ... in order, then a fixed shuffle tree
+  const int lane = threadIdx.x;
+  double m = 0.0, s = 0.0;
+  for (uint32_t g = lane; g < nblocks; g += 32) {
+    m = (pmax[g] > m || pmax[g] != pmax[g]) ? pmax[g] : m;
+    s += psum[g];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double om = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (om > m || om != om) ? om : m;
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if (lane != 0) return;
+  VecScale r;
+  r.sum = s;
+  r.inv_delta_unused = 0.0;
+  r.pad = 0;
+  if (m == 0.0) {
+    r.ex = 0;
+    r.delta = 0.0;
+  } else if (!(m < 1.79e308)) {  // NaN or Inf
+    r.ex = 0;
+    r.delta = nan("");
+  } else {
+    int ex;
+    frexp(m, &ex);  // m = f * 2^ex, 0.5 <= f < 1  ->  |v| < 2^ex
+    r.ex = ex;
+    r.delta = ldexp(1.0, ex - kSliceBits);
+  }
+  *out = r;
+}
+
+// ---------------------------------------------------------------------------
+// Slicing: one thread per word-column (16 consecutive vector elements).
+// out[(wq * 8 + s)] is a uint4 = 16 int8 digits ordered [f][b]: digit s of
+// element 16 wq + 4 b + f, pre-divided by 4^f (see file header).
+// Elements >= n are zero.  nwq = number of word-columns to write.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_slice_vec(const double* __restrict__ v, uint64_t n, uint32_t nwq,
+            const VecScale* __restrict__ sc, uint4* __restrict__ out) {
+  uint32_t wq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wq >= nwq) return;
+  const int ex = sc->ex;
+  const bool live = sc->delta > 0.0;  // false for zero / non-finite vectors
+  uint32_t dig[8][4] = {};
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      uint64_t i = (uint64_t)wq * 16 + 4 * b + f;
+      long long q = 0;
+      if (live && i < n) q = __double2ll_rn(ldexp(v[i], kSliceBits - ex - 2 * f));
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        long long d = (s < 7) ? (((q + 64) & 127) - 64) : q;
+        q = (q - d) >> 7;
+        dig[s][f] |= ((uint32_t)(d & 0xFF)) << (8 * b);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    out[(uint64_t)wq * 8 + s] = make_uint4(dig[s][0], dig[s][1], dig[s][2], dig[s][3]);
+}
+
+// ---------------------------------------------------------------------------
+// The hot kernel.  G: R rows x pitch bytes of packed dosage codes; S: digit
+// slices of the input vector over G's columns.  A CTA of WARPS warps owns
+// 16*WARPS consecutive rows and one split of the column chunks; warp w owns
+// rows [16w, 16w+16) of the CTA tile.  Per chunk (2048 columns):
+//   * the 16 KB slice block of the chunk is brought to shared memory with
+//     cp.async (double buffered, XOR-swizzled so the B-fragment LDS.128 are
+//     bank-conflict free);
+//   * every thread streams its two rows' packed words from HBM with 16-byte
+//     non-allocating loads, prefetched one step ahead;
+//   * 4 LOP3 + 1 LDS.128 feed two mma.sync.m16n8k32.u8.s8 per packed word.
+// out[split * out_stride + row] = sum_s 128^s * D[row][s]  (FP64, exact terms).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+// shared-memory slot (in uint4 units) of slice s of local word-column wl (0..127)
+__device__ __forceinline__ int slice_slot(int wl, int s) {
+  return wl * 8 + ((s + 2 * ((wl >> 2) & 3)) & 7);
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+k_imma_gemv(const uint8_t* __restrict__ G, uint64_t pitch, uint32_t R,
+            const uint4* __restrict__ S, uint32_t nchunks, uint32_t chunks_per_split,
+            double* __restrict__ out, uint64_t out_stride) {
+  __shared__ uint4 sb[3][kChunkWords * 8];  // 3 x 16 KB ring: one barrier per chunk
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t row_a = min(R - 1, (blockIdx.x * WARPS + warp) * 16 + g);
+  const uint32_t row_b = min(R - 1, (blockIdx.x * WARPS + warp) * 16 + g + 8);
+  const uint32_t c_begin = blockIdx.y * chunks_per_split;
+  const uint32_t c_end = min(nchunks, c_begin + chunks_per_split);
+  const uint8_t* pa = G + (uint64_t)row_a * pitch + q * 16;
+  const uint8_t* pb = G + (uint64_t)row_b * pitch + q * 16;
+
+  auto issue_slices = [&](uint32_t chunk, int buf) {
+    const uint4* src = S + (uint64_t)chunk * (kChunkWords * 8);
+    for (int e = tid; e < kChunkWords * 8; e += WARPS * 32)
+      cp_async16(&sb[buf][slice_slot(e >> 3, e & 7)], src + e);
+    cp_async_commit();
+  };
+  // One batch = 4 steps = 256 contiguous bytes of each of the thread's two rows
+  // (the quad's four lanes cover 64 B per step): 8 independent 16-byte loads in
+  // flight per thread, and DRAM sees 256-byte bursts per row.
+  auto load_batch = [&](uint32_t half, uint4 (&wa)[4], uint4 (&wb)[4]) {
+    uint64_t off = (uint64_t)half * 256;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (off + u * 64 + q * 16 < pitch) {
+        wa[u] = ld_stream_u128(reinterpret_cast<const uint4*>(pa + off + u * 64));
+        wb[u] = ld_stream_u128(reinterpret_cast<const uint4*>(pb + off + u * 64));
+      } else {
+        wa[u] = make_uint4(0, 0, 0, 0);
+        wb[u] = wa[u];
+      }
+    }
+  };
+
+  int acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};  // two independent IMMA chains
+  double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c_begin < c_end) {
+    issue_slices(c_begin, 0);
+    if (c_begin + 1 < c_end) issue_slices(c_begin + 1, 1);
+    uint4 na[4], nb[4];
+    load_batch(2 * c_begin, na, nb);
+    for (uint32_t c = c_begin; c < c_end; c++) {
+      const int buf = (c - c_begin) % 3;
+      if (c + 1 < c_end) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      // chunk c's slices have landed for every thread, and every thread has
+      // finished chunk c-1, so ring slot (c+2)%3 == (c-1)%3 may be refilled
+      __syncthreads();
+      if (c + 2 < c_end) issue_slices(c + 2, (buf + 2) % 3);
+      const uint4* sbuf = sb[buf];
+#pragma unroll
+      for (int hb = 0; hb < 2; hb++) {
+        uint4 wa[4], wb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          wa[u] = na[u];
+          wb[u] = nb[u];
+        }
+        if (hb == 0 || c + 1 < c_end) load_batch(2 * c + hb + 1, na, nb);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t xa[4] = {wa[u].x, wa[u].y, wa[u].z, wa[u].w};
+          const uint32_t xb[4] = {wb[u].x, wb[u].y, wb[u].z, wb[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int wl = (hb * 4 + u) * 16 + q * 4 + j;
+            const uint4 bv = sbuf[slice_slot(wl, g)];
+            mma_u8s8(acc0, xa[j] & 0x03030303u, xb[j] & 0x03030303u, xa[j] & 0x0C0C0C0Cu,
+                     xb[j] & 0x0C0C0C0Cu, bv.x, bv.y);
+            mma_u8s8(acc1, xa[j] & 0x30303030u, xb[j] & 0x30303030u, xa[j] & 0xC0C0C0C0u,
+                     xb[j] & 0xC0C0C0C0u, bv.z, bv.w);
+          }
+        }
+      }
+      if (((c - c_begin) % kFlushChunks) == kFlushChunks - 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          dacc[k] += (double)acc0[k] + (double)acc1[k];
+          acc0[k] = 0;
+          acc1[k] = 0;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) dacc[k] += (double)acc0[k] + (double)acc1[k];
+  // c0,c1: row g, slices 2q, 2q+1;  c2,c3: row g+8.  Weight slice s by 128^s.
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+  double ra = dacc[0] * w0 + dacc[1] * w1;
+  double rb = dacc[2] * w0 + dacc[3] * w1;
+  ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+  rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+  ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+  rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+  if (q == 0) {
+    uint32_t r0 = (blockIdx.x * WARPS + warp) * 16 + g;
+    double* o = out + (uint64_t)blockIdx.y * out_stride;
+    if (r0 < R) o[r0] = ra;
+    if (r0 + 8 < R) o[r0 + 8] = rb;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sparse missing-genotype sums: one warp per row of a CSR list,
+//   out[r] = sum over the row's column indices of coef[col]   (fixed order).
+// Runs on the handle's side stream, concurrently with k_imma_gemv.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_csr_gather(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
+             const double* __restrict__ coef, uint64_t nrows, double* __restrict__ out) {
+  uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  uint64_t b = rowptr[r], e = rowptr[r + 1];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  uint64_t k = b + lane;
+  for (; k + 96 < e; k += 128) {
+    uint32_t c0 = colidx[k], c1 = colidx[k + 32], c2 = colidx[k + 64], c3 = colidx[k + 96];
+    s0 += coef[c0];
+    s1 += coef[c1];
+    s2 += coef[c2];
+    s3 += coef[c3];
+  }
+  for (; k < e; k += 32) s0 += coef[colidx[k]];
+  double s = warp_sum((s0 + s1) + (s2 + s3));
+  if (lane == 0) out[r] = s;
+}
+
+// Finalise X'x for SNP j:
+//   E_j = delta * sum_splits part[s][j];   t_j = [(E_j - 3 Mx_j) - mu_j (Sx - Mx_j)] * inv_sd_j
+// t_out (optional) receives t_j; a_out (optional) receives a_j = t_j * inv_sd_j,
+// b_j = mu_j a_j, corr_j = b_j - 3 a_j (inputs of the second half of perform_op).
+// mx may be null (no missing genotypes at all).
+__global__ void __launch_bounds__(256)
+k_finalize_crossprod(const double* __restrict__ part, uint32_t nsplits, uint64_t stride,
+                     uint32_t nsnps, const VecScale* __restrict__ sc,
+                     const double2* __restrict__ scale, const double* __restrict__ mxv,
+                     double* __restrict__ t_out, double* __restrict__ a_out,
+                     double* __restrict__ b_out, double* __restrict__ corr_out) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nsnps) return;
+  double mx = mxv ? mxv[j] : 0.0;
+  double e = 0.0;
+  for (uint32_t s = 0; s < nsplits; s++) e += part[(uint64_t)s * stride + j];
+  e *= sc->delta;
+  double2 ms = scale[j];
+  double t = ((e - 3.0 * mx) - ms.x * (sc->sum - mx)) * ms.y;
+  const bool dead = ms.y == 0.0;  // monomorphic / undefined SNP: zero column (data.cpp:300)
+  if (dead) t = 0.0;
+  if (t_out) t_out[j] = t;
+  if (a_out) {
+    double a = dead ? 0.0 : t * ms.y, b = dead ? 0.0 : ms.x * a;
+    a_out[j] = a;
+    b_out[j] = b;
+    corr_out[j] = b - 3.0 * a;
+  }
+}
+
+// Inputs of prod from a user vector v:  a_j = v_j inv_sd_j, b_j = mu_j a_j, corr_j = b_j - 3 a_j
+__global__ void k_prod_inputs(const double* __restrict__ v, const double2* __restrict__ scale,
+                              uint32_t nsnps, double* __restrict__ a_out,
+                              double* __restrict__ b_out, double* __restrict__ corr_out) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nsnps) return;
+  double2 ms = scale[j];
+  double a = v[j] * ms.y, b = ms.x * a;
+  if (ms.y == 0.0) { a = 0.0; b = 0.0; }
+  a_out[j] = a;
+  b_out[j] = b;
+  corr_out[j] = b - 3.0 * a;
+}
+
+// Finalise X v for individual i:
+//   y_i = delta_a * sum_splits part[s][i] - Sb + mc_i,  mc_i = sum_{j missing} corr_j
+__global__ void __launch_bounds__(256)
+k_finalize_prod(const double* __restrict__ part, uint32_t nsplits, uint64_t stride, uint64_t n,
+                const VecScale* __restrict__ sc_a, const VecScale* __restrict__ sc_b,
+                const double* __restrict__ mcv, double* __restrict__ y) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double f = 0.0;
+  for (uint32_t s = 0; s < nsplits; s++) f += part[(uint64_t)s * stride + i];
+  y[i] = f * sc_a->delta - sc_b->sum + (mcv ? mcv[i] : 0.0);
+}
+
+}  // namespace fpb

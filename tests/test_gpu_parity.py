@@ -22,6 +22,14 @@ def _mk(payload, n, p, **kw):
     return SVDWideOnline(payload=payload, n=n, nsnps=p, **kw)
 
 
+@pytest.fixture(params=["imma", "generic"])
+def path(request, monkeypatch):
+    """Both compute paths of the library: the int8 tensor-core path and the
+    generic FP64 path (FPB_PATH is read when an operator is created)."""
+    monkeypatch.setenv("FPB_PATH", request.param)
+    return request.param
+
+
 def _relerr(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
@@ -39,7 +47,7 @@ def _pack(codes):
 
 @pytest.mark.parametrize("name", ["data_chr1", "hapmap3"])
 @pytest.mark.parametrize("stand", [O.STANDARDISE_BINOM2, O.STANDARDISE_BINOM])
-def test_fixture_operator_family(native_lib, name, stand):
+def test_fixture_operator_family(native_lib, path, name, stand):
     _, payload, n, p = load_fixture(name)
     op = _mk(payload, n, p, stand_method=stand)
     orc = O.COracle(payload, n, p, stand)
@@ -76,7 +84,7 @@ def test_reference_block_order_vs_one_pass(native_lib):
 
 @pytest.mark.parametrize("n,p", [(1, 3), (3, 1), (4, 5), (63, 9), (64, 64), (65, 130), (1000, 17),
                                  (4099, 257), (16384 + 5, 40)])
-def test_ragged_shapes(native_lib, n, p):
+def test_ragged_shapes(native_lib, path, n, p):
     """N not a multiple of 4/16/64 (pad genotypes must contribute 0), tiny and
     ragged shapes, heavy missingness."""
     rng = np.random.default_rng(n * 1000 + p)
@@ -104,7 +112,7 @@ def test_ragged_shapes(native_lib, n, p):
     op.close()
 
 
-def test_monomorphic_and_all_missing_columns(native_lib):
+def test_monomorphic_and_all_missing_columns(native_lib, path):
     n, p = 37, 6
     rng = np.random.default_rng(3)
     codes = np.full((n, p), 3, dtype=np.uint8)
@@ -122,7 +130,7 @@ def test_monomorphic_and_all_missing_columns(native_lib):
     assert abs(op.trace - orc.trace) <= 1e-12 * orc.trace
 
 
-def test_preloaded_meansd(native_lib):
+def test_preloaded_meansd(native_lib, path):
     """Data::use_preloaded_maf (data.cpp:293-297) with maf2meansd's sd
     (randompca.cpp:745-751: 2p(1-p), no sqrt)."""
     _, payload, n, p = load_fixture("data_chr1")
@@ -137,7 +145,7 @@ def test_preloaded_meansd(native_lib):
     assert np.array_equal(op.meansd(), pre)
 
 
-def test_create_from_file_and_shards(native_lib):
+def test_create_from_file_and_shards(native_lib, path):
     from flashpca_b200 import Data, SVDWideOnline
     stem = FIXTURES["data_chr1"]
     d = Data()
@@ -159,6 +167,30 @@ def test_create_from_file_and_shards(native_lib):
     assert _relerr(a.perform_op(x) + b.perform_op(x), y_ref) <= OP_RTOL
     assert abs(a.trace + b.trace - orc.trace) <= 1e-12 * orc.trace
     assert np.array_equal(np.concatenate([a.meansd(), b.meansd()]), orc.meansd())
+
+
+def test_tensor_path_is_deterministic_and_default(native_lib, monkeypatch):
+    """Low-missingness data takes the tensor path by default; its integer
+    accumulation makes repeated calls bit-identical, and it agrees with the
+    generic FP64 path to OP_RTOL."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    _, payload, n, p = load_fixture("hapmap3")
+    op = _mk(payload, n, p)
+    x = np.random.default_rng(21).standard_normal(n)
+    y1, y2 = op.perform_op(x), op.perform_op(x)
+    assert np.array_equal(y1, y2)
+    monkeypatch.setenv("FPB_PATH", "generic")
+    og = _mk(payload, n, p)
+    assert _relerr(y1, og.perform_op(x)) <= OP_RTOL
+    # scale invariance of the fixed-point conversion: tiny, huge and zero vectors
+    for sc in (1e-300, 1e-30, 1e30, 1e250):
+        assert _relerr(op.perform_op(x * sc) / sc, y1) <= OP_RTOL
+    assert np.all(op.perform_op(np.zeros(n)) == 0.0)
+    e = np.zeros(n)
+    e[17] = 1.0
+    orc = O.COracle(payload, n, p)
+    assert _relerr(op.perform_op(e), orc.perform_op(e, 0)) <= OP_RTOL
+    assert np.isnan(op.perform_op(np.full(n, np.nan))).all()
 
 
 def test_error_paths(native_lib):
@@ -240,7 +272,7 @@ def test_pca_vs_dense_eigh(native_lib, name, ndim):
     assert np.abs(r3.Px - r2.Px).max() < 1e-5 * np.abs(r2.Px).max()
 
 
-def test_gpu_solver_vs_oracle_solver_same_tol(native_lib):
+def test_gpu_solver_vs_oracle_solver_same_tol(native_lib, path):
     """Device IRLM and the oracle's Spectra restatement, same start vector and
     tolerance, on the C oracle operator vs the CUDA operator."""
     _, payload, n, p = load_fixture("data_chr1")
