@@ -13,6 +13,7 @@
 // No CPU fallback exists: if CUDA is unusable every entry point fails.
 #include "../../include/flashpca_b200.h"
 
+#include <cuda.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <errno.h>
@@ -109,6 +110,10 @@ struct fpb_handle {
   double *d_mx = nullptr, *d_mc = nullptr;  // per-SNP / per-individual missing-genotype sums
   fpb::VecScale* d_sc = nullptr;  // [0] = x, [1] = a, [2] = b
   uint32_t nchunks_s = 0, nchunks_i = 0, splits_s = 1, splits_i = 1, cps_s = 1, cps_i = 1;
+  // TMA kernel variant: tensor maps over gs / gi, 128-byte stages
+  bool use_tma = false;
+  fpb::TmaDesc tm_s, tm_i;
+  uint32_t nstages_s = 0, nstages_i = 0, tsplits_s = 1, tsplits_i = 1, sps_s = 1, sps_i = 1;
   uint64_t part_stride = 0;
   // host-pointer API staging (grown on demand)
   double* d_in = nullptr;
@@ -184,8 +189,12 @@ int alloc_common(fpb_handle* h, uint64_t n, uint64_t nsnps, int stand_method, in
   cudaDeviceProp prop;
   FPB_CUDA(h, cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
-  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  // the contraction runs on a high-priority stream; the sparse missing-genotype
+  // gathers fill the SM resources it leaves free from a low-priority side stream
+  int prio_lo = 0, prio_hi = 0;
+  FPB_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  FPB_CUDA(h, cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+  FPB_CUDA(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo));
   FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->n = n;
@@ -235,6 +244,47 @@ void pick_splits(uint32_t rows, uint32_t nchunks, int sm_count, uint32_t* splits
   s = std::max<uint32_t>(1, std::min<uint32_t>(s, 64));
   *cps = (nchunks + s - 1) / s;
   *splits = (nchunks + *cps - 1) / *cps;
+}
+
+void pick_splits_tma(uint32_t rows, uint32_t nstages, int sm_count, uint32_t* splits,
+                     uint32_t* sps) {
+  uint32_t tiles = (rows + fpb::kTmaRows - 1) / fpb::kTmaRows;
+  uint32_t want = (20u * sm_count + tiles - 1) / tiles;  // 1 CTA per SM resident
+  uint32_t s = std::min<uint32_t>(want, std::max<uint32_t>(1, nstages / 32));
+  s = std::max<uint32_t>(1, std::min<uint32_t>(s, 64));
+  *sps = (nstages + s - 1) / s;
+  *splits = (nstages + *sps - 1) / *sps;
+}
+
+// 2-D uint8 tensor map over a packed matrix: dim0 = bytes of a row, dim1 = rows;
+// box = 128 B x 256 rows, 128-byte swizzle, out-of-bounds filled with zeros.
+int make_tensor_map(fpb_handle* h, const uint8_t* base, uint64_t pitch, uint64_t rows,
+                    fpb::TmaDesc* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                               const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FPB_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+      FPB_FAIL(h, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (EncodeFn)fn;
+  }
+  static_assert(sizeof(CUtensorMap) == sizeof(fpb::TmaDesc), "tensor map size");
+  cuuint64_t dims[2] = {pitch, rows};
+  cuuint64_t strides[1] = {pitch};
+  cuuint32_t box[2] = {(cuuint32_t)fpb::kTmaStageCols, (cuuint32_t)fpb::kTmaRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                       const_cast<uint8_t*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS)
+    FPB_FAIL(h, std::string("cuTensorMapEncodeTiled failed, code ") + std::to_string((int)rc));
+  return 0;
 }
 
 // raw bed bytes are in d_gs (pitch_s): recode, statistics (data.cpp:257-322),
@@ -314,10 +364,27 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
   pick_splits((uint32_t)h->nsnps, h->nchunks_s, h->sm_count, &h->splits_s, &h->cps_s);
   pick_splits((uint32_t)h->n, h->nchunks_i, h->sm_count, &h->splits_i, &h->cps_i);
   h->part_stride = std::max(h->n, h->nsnps);
+  {
+    const char* gv = getenv("FPB_GEMV");
+    h->use_tma = !(gv && !strcmp(gv, "ldg"));
+    h->nstages_s = (uint32_t)((h->pitch_s + fpb::kTmaStageCols - 1) / fpb::kTmaStageCols);
+    h->nstages_i = (uint32_t)((h->pitch_i + fpb::kTmaStageCols - 1) / fpb::kTmaStageCols);
+    pick_splits_tma((uint32_t)h->nsnps, h->nstages_s, h->sm_count, &h->tsplits_s, &h->sps_s);
+    pick_splits_tma((uint32_t)h->n, h->nstages_i, h->sm_count, &h->tsplits_i, &h->sps_i);
+    if (h->use_tma) {
+      if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_s)) return 1;
+      if (make_tensor_map(h, h->d_gi, h->pitch_i, h->n, &h->tm_i)) return 1;
+      FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fpb::kTmaSmemBytes));
+    }
+  }
   uint64_t max_chunks = std::max(h->nchunks_s, h->nchunks_i);
   FPB_CUDA(h, cudaMalloc(&h->d_slices, sizeof(uint4) * max_chunks * fpb::kChunkWords * 8));
-  FPB_CUDA(h, cudaMalloc(&h->d_part, sizeof(double) * h->part_stride *
-                                         std::max(h->splits_s, h->splits_i)));
+  FPB_CUDA(h, cudaMalloc(&h->d_part,
+                         sizeof(double) * h->part_stride *
+                             std::max(std::max(h->splits_s, h->splits_i),
+                                      std::max(h->tsplits_s, h->tsplits_i))));
   FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * h->nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_b, sizeof(double) * h->nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * h->nsnps));
@@ -392,25 +459,45 @@ void vec_prepare(fpb_handle* h, const double* d_v, uint64_t len, int slot) {
   h->launches += 2;
 }
 
-// part[split][row] = sum_s 128^s sum_col G[row][col] * digit_s(v[col])
-void imma_contract(fpb_handle* h, const uint8_t* G, uint64_t pitch, uint32_t rows,
-                   const double* d_v, uint64_t vlen, int slot, uint32_t nchunks, uint32_t splits,
-                   uint32_t cps) {
-  uint32_t nwq = nchunks * fpb::kChunkWords;
+// part[split][row] = sum_s 128^s sum_col G[row][col] * digit_s(v[col]);
+// snp_major selects gs (rows = SNPs) or gi (rows = individuals).  Returns the
+// number of splits written.
+uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_t vlen, int slot) {
+  const uint8_t* G = snp_major ? h->d_gs : h->d_gi;
+  const uint64_t pitch = snp_major ? h->pitch_s : h->pitch_i;
+  const uint32_t rows = (uint32_t)(snp_major ? h->nsnps : h->n);
+  const uint32_t nchunks = snp_major ? h->nchunks_s : h->nchunks_i;
+  uint32_t nwq = nchunks * fpb::kChunkWords;  // covers the TMA stages as well
   fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(d_v, vlen, nwq, h->d_sc + slot,
                                                              h->d_slices);
+  h->launches += 2;
+  if (h->use_tma) {
+    const uint32_t nstages = snp_major ? h->nstages_s : h->nstages_i;
+    const uint32_t splits = snp_major ? h->tsplits_s : h->tsplits_i;
+    const uint32_t sps = snp_major ? h->sps_s : h->sps_i;
+    dim3 grid((rows + fpb::kTmaRows - 1) / fpb::kTmaRows, splits);
+    fpb::k_imma_gemv_tma<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
+                           h->stream>>>(snp_major ? h->tm_s : h->tm_i, rows, h->d_slices, nstages,
+                                        sps, h->d_part, h->part_stride);
+    return splits;
+  }
+  const uint32_t splits = snp_major ? h->splits_s : h->splits_i;
+  const uint32_t cps = snp_major ? h->cps_s : h->cps_i;
   dim3 grid((rows + 16 * kWarps - 1) / (16 * kWarps), splits);
   fpb::k_imma_gemv<kWarps><<<grid, kWarps * 32, 0, h->stream>>>(G, pitch, rows, h->d_slices,
                                                                 nchunks, cps, h->d_part,
                                                                 h->part_stride);
-  h->launches += 2;
+  return splits;
 }
 
-// out[r] = sum of coef over the missing entries of row r, on the side stream
-// (forked after everything already enqueued on the main stream)
-void fork_gather(fpb_handle* h, const uint64_t* rowptr, const uint32_t* colidx,
-                 const double* coef, uint64_t nrows, double* out) {
-  cudaEventRecord(h->ev_fork, h->stream);
+// Sparse missing-genotype sums on the side stream.  fork_mark() pins the point
+// of the main stream the gather depends on (its input vector is complete);
+// gather_launch() is called AFTER the contraction kernel has been enqueued so
+// the block scheduler places the big kernel first and back-fills with gather
+// blocks; join_gather() makes the main stream wait for the result.
+void fork_mark(fpb_handle* h) { cudaEventRecord(h->ev_fork, h->stream); }
+void gather_launch(fpb_handle* h, const uint64_t* rowptr, const uint32_t* colidx,
+                   const double* coef, uint64_t nrows, double* out) {
   cudaStreamWaitEvent(h->side, h->ev_fork, 0);
   uint32_t gb = (uint32_t)((nrows * 32 + 255) / 256);
   fpb::k_csr_gather<<<gb, 256, 0, h->side>>>(rowptr, colidx, coef, nrows, out);
@@ -421,28 +508,32 @@ void join_gather(fpb_handle* h) { cudaStreamWaitEvent(h->stream, h->ev_join, 0);
 
 // first half: t = X'x (d_t) and/or the a, b, corr inputs of the second half
 void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_half) {
-  if (h->nmissing) fork_gather(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
+  if (h->nmissing) fork_mark(h);
   vec_prepare(h, d_x, h->n, 0);
-  imma_contract(h, h->d_gs, h->pitch_s, (uint32_t)h->nsnps, d_x, h->n, 0, h->nchunks_s,
-                h->splits_s, h->cps_s);
-  if (h->nmissing) join_gather(h);
+  const uint32_t nsplits = imma_contract(h, true, d_x, h->n, 0);
+  if (h->nmissing) {
+    gather_launch(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
+    join_gather(h);
+  }
   uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
   fpb::k_finalize_crossprod<<<gb, 256, 0, h->stream>>>(
-      h->d_part, h->splits_s, h->part_stride, (uint32_t)h->nsnps, h->d_sc + 0, h->d_scale,
+      h->d_part, nsplits, h->part_stride, (uint32_t)h->nsnps, h->d_sc + 0, h->d_scale,
       h->nmissing ? h->d_mx : nullptr, d_t, second_half ? h->d_a : nullptr, h->d_b, h->d_corr);
   h->launches++;
 }
 
 // second half from a, b, corr already in the handle: y = F - Sb + missing terms
 void imma_prod_tail(fpb_handle* h, double* d_y) {
-  if (h->nmissing) fork_gather(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
+  if (h->nmissing) fork_mark(h);
   vec_prepare(h, h->d_a, h->nsnps, 1);
   vec_prepare(h, h->d_b, h->nsnps, 2);
-  imma_contract(h, h->d_gi, h->pitch_i, (uint32_t)h->n, h->d_a, h->nsnps, 1, h->nchunks_i,
-                h->splits_i, h->cps_i);
-  if (h->nmissing) join_gather(h);
+  const uint32_t nsplits = imma_contract(h, false, h->d_a, h->nsnps, 1);
+  if (h->nmissing) {
+    gather_launch(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
+    join_gather(h);
+  }
   uint32_t gb = (uint32_t)((h->n + 255) / 256);
-  fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, h->splits_i, h->part_stride, h->n,
+  fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, nsplits, h->part_stride, h->n,
                                                   h->d_sc + 1, h->d_sc + 2,
                                                   h->nmissing ? h->d_mc : nullptr, d_y);
   h->launches++;

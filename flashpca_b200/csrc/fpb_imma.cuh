@@ -125,8 +125,11 @@ __global__ void k_vec_final(const double* __restrict__ pmax, const double* __res
 
 // ---------------------------------------------------------------------------
 // Slicing: one thread per word-column (16 consecutive vector elements).
-// out[(wq * 8 + s)] is a uint4 = 16 int8 digits ordered [f][b]: digit s of
-// element 16 wq + 4 b + f, pre-divided by 4^f (see file header).
+// out[wq * 8 + slice_slot(wq, s)] is a uint4 = 16 int8 digits ordered [f][b]:
+// digit s of element 16 wq + 4 b + f, pre-divided by 4^f (see file header).  The
+// 8 slices of a word-column are rotated by 2*((wq>>2)&3) so that the B-fragment
+// LDS.128 of the contraction kernels (lanes g = slice, q = word-column group)
+// are bank-conflict free when the block is copied verbatim to shared memory.
 // Elements >= n are zero.  nwq = number of word-columns to write.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -154,7 +157,8 @@ k_slice_vec(const double* __restrict__ v, uint64_t n, uint32_t nwq,
   }
 #pragma unroll
   for (int s = 0; s < 8; s++)
-    out[(uint64_t)wq * 8 + s] = make_uint4(dig[s][0], dig[s][1], dig[s][2], dig[s][3]);
+    out[(uint64_t)wq * 8 + ((s + 2 * ((wq >> 2) & 3)) & 7)] =
+        make_uint4(dig[s][0], dig[s][1], dig[s][2], dig[s][3]);
 }
 
 // ---------------------------------------------------------------------------
@@ -189,7 +193,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
-// shared-memory slot (in uint4 units) of slice s of local word-column wl (0..127)
+// slot (in uint4 units) of slice s of local word-column wl inside a slice block
 __device__ __forceinline__ int slice_slot(int wl, int s) {
   return wl * 8 + ((s + 2 * ((wl >> 2) & 3)) & 7);
 }
@@ -212,7 +216,7 @@ k_imma_gemv(const uint8_t* __restrict__ G, uint64_t pitch, uint32_t R,
   auto issue_slices = [&](uint32_t chunk, int buf) {
     const uint4* src = S + (uint64_t)chunk * (kChunkWords * 8);
     for (int e = tid; e < kChunkWords * 8; e += WARPS * 32)
-      cp_async16(&sb[buf][slice_slot(e >> 3, e & 7)], src + e);
+      cp_async16(&sb[buf][e], src + e);
     cp_async_commit();
   };
   // One batch = 4 steps = 256 contiguous bytes of each of the thread's two rows
@@ -297,6 +301,198 @@ k_imma_gemv(const uint8_t* __restrict__ G, uint64_t pitch, uint32_t R,
     double* o = out + (uint64_t)blockIdx.y * out_stride;
     if (r0 < R) o[r0] = ra;
     if (r0 + 8 < R) o[r0 + 8] = rb;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The hot kernel, TMA version.  Same maths and fragment mapping as k_imma_gemv;
+// the packed genotypes and the digit slices reach shared memory through the
+// async proxy instead of registers:
+//   * one producer thread issues, per stage, a 2-D cp.async.bulk.tensor of a
+//     [256 rows x 128 B] genotype tile (SWIZZLE_128B) and a 4 KB bulk copy of
+//     the matching slice block, both completing on the stage's "full" mbarrier;
+//   * 8 consumer warps (32 rows each, i.e. two m16 tiles sharing every
+//     B-fragment) wait on "full", run 32 IMMAs per stage and release the stage
+//     through its "empty" mbarrier -- no CTA-wide barrier in the main loop;
+//   * kTmaStages x 36 KB are in flight per SM without holding registers.
+// MMA row g of a tile is matrix row rho(g) = (g>>1) | ((g&1)<<2) of the tile so
+// that the two rows read by a quarter-warp differ in address bit 9..7 ^ bit 2
+// and the swizzled LDS.128 are bank-conflict free.
+// ---------------------------------------------------------------------------
+constexpr int kTmaStages = 5;
+constexpr int kTmaRows = 256;                       // rows per CTA tile
+constexpr int kTmaStageCols = 128;                  // packed bytes per row per stage (512 columns)
+constexpr int kTmaTileBytes = kTmaRows * kTmaStageCols;          // 32 KB
+constexpr int kTmaSliceBytes = (kTmaStageCols / 4) * 8 * 16;     // 32 word-columns x 8 slices = 4 KB
+constexpr int kTmaStageBytes = kTmaTileBytes + kTmaSliceBytes;   // 36 KB
+constexpr int kTmaSmemBytes = kTmaStages * kTmaStageBytes + 1024 + 128;
+constexpr int kTmaConsumerWarps = 8;
+constexpr int kTmaFlushStages = 96;                 // int32 -> FP64 every 49152 columns
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int x, int y,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes,
+                                          uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+struct alignas(64) TmaDesc {  // CUtensorMap is an opaque 128-byte, 64-byte aligned blob
+  unsigned long long opaque[16];
+};
+
+__global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
+k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* __restrict__ S,
+                uint32_t nstages, uint32_t stages_per_split, double* __restrict__ out,
+                uint64_t out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B: 1 KB aligned
+  const uint32_t bars = base + kTmaStages * kTmaStageBytes;       // full[], then empty[]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t s_begin = blockIdx.y * stages_per_split;
+  const uint32_t s_end = min(nstages, s_begin + stages_per_split);
+  const uint32_t nst = s_end > s_begin ? s_end - s_begin : 0;
+  const uint32_t row0 = blockIdx.x * kTmaRows;
+
+  if (tid == 0) {
+    for (int i = 0; i < kTmaStages; i++) {
+      mbar_init(bars + 8 * i, 1);                                 // full: producer + tx bytes
+      mbar_init(bars + 8 * (kTmaStages + i), kTmaConsumerWarps);  // empty: one arrive per warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumerWarps) {
+    // ------------------------------ producer ------------------------------
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      for (uint32_t it = 0; it < nst; it++) {
+        const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+        const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTmaStages + slot);
+        if (round > 0) mbar_wait(empty, (round - 1) & 1);
+        const uint32_t dst = base + slot * kTmaStageBytes;
+        mbar_expect_tx(full, kTmaStageBytes);
+        tma_load_2d(dst, &tmap, (int)((s_begin + it) * kTmaStageCols), (int)row0, full);
+        bulk_load(dst + kTmaTileBytes,
+                  S + (uint64_t)(s_begin + it) * (kTmaSliceBytes / 16), kTmaSliceBytes, full);
+      }
+    }
+    return;
+  }
+
+  // -------------------------------- consumers -------------------------------
+  const int g = lane >> 2, q = lane & 3;
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  // byte offsets inside a stage tile of this thread's four rows (tile t, half h)
+  uint32_t roff[2][2];
+#pragma unroll
+  for (int t = 0; t < 2; t++)
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) roff[t][hf] = (uint32_t)(warp * 32 + t * 16 + hf * 8 + rho) * 128u;
+  const uint32_t rx = (uint32_t)(rho & 7);  // (row & 7) of all four rows
+
+  int acc[2][2][4] = {};      // [tile][chain][frag]
+  double dacc[2][4] = {};
+  for (uint32_t it = 0; it < nst; it++) {
+    const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+    mbar_wait(bars + 8 * slot, round & 1);
+    const uint32_t tile = base + slot * kTmaStageBytes;
+    const uint32_t sl = tile + kTmaTileBytes;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t chunk = ((uint32_t)(u * 4 + q) ^ rx) << 4;
+      uint4 w[2][2];
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++)
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(w[t][hf].x), "=r"(w[t][hf].y), "=r"(w[t][hf].z), "=r"(w[t][hf].w)
+                       : "r"(tile + roff[t][hf] + chunk));
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int wl = u * 16 + q * 4 + j;
+        uint4 bv;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(bv.x), "=r"(bv.y), "=r"(bv.z), "=r"(bv.w)
+                     : "r"(sl + (uint32_t)slice_slot(wl, g) * 16u));
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const uint32_t xa = j == 0 ? w[t][0].x : j == 1 ? w[t][0].y : j == 2 ? w[t][0].z : w[t][0].w;
+          const uint32_t xb = j == 0 ? w[t][1].x : j == 1 ? w[t][1].y : j == 2 ? w[t][1].z : w[t][1].w;
+          mma_u8s8(acc[t][0], xa & 0x03030303u, xb & 0x03030303u, xa & 0x0C0C0C0Cu,
+                   xb & 0x0C0C0C0Cu, bv.x, bv.y);
+          mma_u8s8(acc[t][1], xa & 0x30303030u, xb & 0x30303030u, xa & 0xC0C0C0C0u,
+                   xb & 0xC0C0C0C0u, bv.z, bv.w);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8 * (kTmaStages + slot));
+    if ((it % kTmaFlushStages) == kTmaFlushStages - 1) {
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          dacc[t][k] += (double)acc[t][0][k] + (double)acc[t][1][k];
+          acc[t][0][k] = 0;
+          acc[t][1][k] = 0;
+        }
+    }
+  }
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+  double* o = out + (uint64_t)blockIdx.y * out_stride;
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) dacc[t][k] += (double)acc[t][0][k] + (double)acc[t][1][k];
+    double ra = dacc[t][0] * w0 + dacc[t][1] * w1;
+    double rb = dacc[t][2] * w0 + dacc[t][3] * w1;
+    ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+    rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+    ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+    rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+    if (q == 0) {
+      uint32_t r = row0 + warp * 32 + t * 16 + rho;
+      if (r < R) o[r] = ra;
+      if (r + 8 < R) o[r + 8] = rb;
+    }
   }
 }
 
