@@ -189,12 +189,11 @@ int alloc_common(fpb_handle* h, uint64_t n, uint64_t nsnps, int stand_method, in
   cudaDeviceProp prop;
   FPB_CUDA(h, cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
-  // the contraction runs on a high-priority stream; the sparse missing-genotype
-  // gathers fill the SM resources it leaves free from a low-priority side stream
-  int prio_lo = 0, prio_hi = 0;
-  FPB_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  FPB_CUDA(h, cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
-  FPB_CUDA(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo));
+  // main stream: everything ordered; side stream: the sparse missing-genotype
+  // gathers (they only depend on the input vector, so they run ahead of the
+  // contraction kernel and join before the finalize step)
+  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->n = n;
@@ -492,9 +491,8 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
 
 // Sparse missing-genotype sums on the side stream.  fork_mark() pins the point
 // of the main stream the gather depends on (its input vector is complete);
-// gather_launch() is called AFTER the contraction kernel has been enqueued so
-// the block scheduler places the big kernel first and back-fills with gather
-// blocks; join_gather() makes the main stream wait for the result.
+// gather_launch() enqueues it; join_gather() makes the main stream wait for the
+// result before the finalize kernel.
 void fork_mark(fpb_handle* h) { cudaEventRecord(h->ev_fork, h->stream); }
 void gather_launch(fpb_handle* h, const uint64_t* rowptr, const uint32_t* colidx,
                    const double* coef, uint64_t nrows, double* out) {
@@ -508,11 +506,13 @@ void join_gather(fpb_handle* h) { cudaStreamWaitEvent(h->stream, h->ev_join, 0);
 
 // first half: t = X'x (d_t) and/or the a, b, corr inputs of the second half
 void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_half) {
+  const bool gfirst = true;
   if (h->nmissing) fork_mark(h);
+  if (h->nmissing && gfirst) gather_launch(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
   vec_prepare(h, d_x, h->n, 0);
   const uint32_t nsplits = imma_contract(h, true, d_x, h->n, 0);
   if (h->nmissing) {
-    gather_launch(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
+    if (!gfirst) gather_launch(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
     join_gather(h);
   }
   uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
@@ -524,12 +524,14 @@ void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_h
 
 // second half from a, b, corr already in the handle: y = F - Sb + missing terms
 void imma_prod_tail(fpb_handle* h, double* d_y) {
+  const bool gfirst = true;
   if (h->nmissing) fork_mark(h);
+  if (h->nmissing && gfirst) gather_launch(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
   vec_prepare(h, h->d_a, h->nsnps, 1);
   vec_prepare(h, h->d_b, h->nsnps, 2);
   const uint32_t nsplits = imma_contract(h, false, h->d_a, h->nsnps, 1);
   if (h->nmissing) {
-    gather_launch(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
+    if (!gfirst) gather_launch(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
     join_gather(h);
   }
   uint32_t gb = (uint32_t)((h->n + 255) / 256);

@@ -319,13 +319,22 @@ k_imma_gemv(const uint8_t* __restrict__ G, uint64_t pitch, uint32_t R,
 // that the two rows read by a quarter-warp differ in address bit 9..7 ^ bit 2
 // and the swizzled LDS.128 are bank-conflict free.
 // ---------------------------------------------------------------------------
-constexpr int kTmaStages = 5;
+constexpr int kTmaStages = 6;
 constexpr int kTmaRows = 256;                       // rows per CTA tile
 constexpr int kTmaStageCols = 128;                  // packed bytes per row per stage (512 columns)
 constexpr int kTmaTileBytes = kTmaRows * kTmaStageCols;          // 32 KB
 constexpr int kTmaSliceBytes = (kTmaStageCols / 4) * 8 * 16;     // 32 word-columns x 8 slices = 4 KB
 constexpr int kTmaStageBytes = kTmaTileBytes + kTmaSliceBytes;   // 36 KB
-constexpr int kTmaSmemBytes = kTmaStages * kTmaStageBytes + 1024 + 128;
+// The kernel asks for the whole opt-in shared memory of the SM (232448 B), more
+// than the 6 x 36 KB ring + alignment slack + barriers need.  Together with the
+// 1 KB the hardware reserves per resident CTA this leaves no room for a CTA of
+// any other kernel on the same SM: results were observed to be corrupted
+// (per consumer warp, nondeterministically) whenever blocks of another kernel
+// were co-resident with this kernel's CTA, so co-residency is ruled out by
+// construction (profiles/r01_notes.md).
+constexpr int kTmaSmemUsed = kTmaStages * kTmaStageBytes + 1024 + 128;
+constexpr int kTmaSmemBytes = 232448;
+static_assert(kTmaSmemUsed <= kTmaSmemBytes, "TMA ring does not fit in shared memory");
 constexpr int kTmaConsumerWarps = 8;
 constexpr int kTmaFlushStages = 96;                 // int32 -> FP64 every 49152 columns
 

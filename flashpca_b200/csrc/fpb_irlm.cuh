@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstring>
 #include <functional>
 #include <numeric>
 #include <string>
@@ -63,13 +64,65 @@ k_gemv_t_partial(const double* __restrict__ V, uint64_t ld, uint32_t m,
   }
 }
 
-__global__ void k_gemv_t_final(const double* __restrict__ partial, uint32_t nblocks, uint32_t m,
-                               double* __restrict__ out) {
-  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+// out[c] = sum_g partial[g * m + c]; one warp per column, fixed summation order
+__global__ void __launch_bounds__(256)
+k_gemv_t_final(const double* __restrict__ partial, uint32_t nblocks, uint32_t m,
+               double* __restrict__ out) {
+  uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
   if (c >= m) return;
   double s = 0.0;
-  for (uint32_t g = 0; g < nblocks; g++) s += partial[(uint64_t)g * m + c];
-  out[c] = s;
+  for (uint32_t g = lane; g < nblocks; g += 32) s += partial[(uint64_t)g * m + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[c] = s;
+}
+
+// One pass over V[:, :m] per re-orthogonalisation step (256 rows per block, a
+// row per thread kept in registers):
+//   f[r]  = fin[r] - sum_c V[r,c] h[c]          (h may be null: f = fin)
+//   partial[g][c] = sum_{r in block g} V[r,c] f[r]   (c < m),  partial[g][m] = sum f[r]^2
+template <int MAXM>
+__global__ void __launch_bounds__(256)
+k_fused_reorth(const double* __restrict__ V, uint64_t ld, uint32_t m, const double* __restrict__ h,
+               const double* fin, double* f, uint64_t n, double* __restrict__ partial) {
+  __shared__ double hs[MAXM];
+  __shared__ double red[8][MAXM + 1];
+  if (h)
+    for (uint32_t c = threadIdx.x; c < m; c += 256) hs[c] = h[c];
+  __syncthreads();
+  const uint64_t r = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool valid = r < n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double vr[MAXM];
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < MAXM; c++) {
+    vr[c] = (valid && (uint32_t)c < m) ? V[r + (uint64_t)c * ld] : 0.0;
+    if (h && (uint32_t)c < m) s += vr[c] * hs[c];
+  }
+  const double fn = valid ? fin[r] - s : 0.0;
+  if (valid) f[r] = fn;
+#pragma unroll
+  for (int c = 0; c < MAXM; c++) {
+    if ((uint32_t)c < m) {
+      double p = vr[c] * fn;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (lane == 0) red[warp][c] = p;
+    }
+  }
+  double nn = fn * fn;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+  if (lane == 0) red[warp][m] = nn;
+  __syncthreads();
+  for (uint32_t c = threadIdx.x; c <= m; c += 256) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += red[w][c];
+    partial[(uint64_t)blockIdx.x * (m + 1) + c] = t;
+  }
 }
 
 // f[r] -= sum_c V[r + c*ld] * h[c]
@@ -294,6 +347,8 @@ class Irlm {
     gemv_t(f, 1, f, &s);
     return sqrt(s);
   }
+  // fused pass: f = fin - V[:, :m] h (h_host may be null), returns V'f in vf[0..m) and ||f||
+  double reorth_pass(uint32_t m, const double* h_host, const double* fin, double* vf);
   void factorize_from(uint32_t from_k, uint32_t to_m);
   void retrieve_ritzpair();
   // d_out (N x nc) = V (N x ncv) * dQ (ncv x nc)
@@ -315,7 +370,9 @@ class Irlm {
   std::function<void(const double*, double*)> op_;
   double *dV_ = nullptr, *dF_ = nullptr, *dW_ = nullptr, *dVs_ = nullptr, *dPartial_ = nullptr,
          *dSmall_ = nullptr, *dQ_ = nullptr;
-  uint32_t nblocks_ = 0;
+  uint32_t nblocks_ = 0, nblocks256_ = 0;
+  double *dPartial2_ = nullptr, *dH_ = nullptr, *hPinned_ = nullptr;
+  bool fused_ = false;
   std::vector<double> H_, ritz_val_, ritz_est_, ritz_vec_;  // ritz_vec_: ncv x nev
   double beta_ = 0.0;
   uint32_t nops_ = 0;
@@ -329,8 +386,13 @@ inline void Irlm::alloc() {
   cudaMalloc(&dF_, sizeof(double) * n_);
   cudaMalloc(&dW_, sizeof(double) * n_);
   cudaMalloc(&dPartial_, sizeof(double) * (size_t)nblocks_ * ncv_);
-  cudaMalloc(&dSmall_, sizeof(double) * ncv_);
+  cudaMalloc(&dSmall_, sizeof(double) * (ncv_ + 1));
   cudaMalloc(&dQ_, sizeof(double) * ncv_ * ncv_);
+  fused_ = ncv_ <= 48;
+  nblocks256_ = (uint32_t)((n_ + 255) / 256);
+  cudaMalloc(&dPartial2_, sizeof(double) * (size_t)nblocks256_ * (ncv_ + 1));
+  cudaMalloc(&dH_, sizeof(double) * (ncv_ + 1));
+  cudaMallocHost(&hPinned_, sizeof(double) * (ncv_ + 1));
   cudaMemsetAsync(dV_, 0, sizeof(double) * n_ * ncv_, stream_);
   H_.assign((size_t)ncv_ * ncv_, 0.0);
 }
@@ -338,14 +400,31 @@ inline void Irlm::alloc() {
 inline void Irlm::release() {
   cudaFree(dV_); cudaFree(dVs_); cudaFree(dF_); cudaFree(dW_);
   cudaFree(dPartial_); cudaFree(dSmall_); cudaFree(dQ_);
-  dV_ = dVs_ = dF_ = dW_ = dPartial_ = dSmall_ = dQ_ = nullptr;
+  cudaFree(dPartial2_); cudaFree(dH_);
+  if (hPinned_) cudaFreeHost(hPinned_);
+  dV_ = dVs_ = dF_ = dW_ = dPartial_ = dSmall_ = dQ_ = dPartial2_ = dH_ = hPinned_ = nullptr;
 }
 
 inline void Irlm::gemv_t(const double* V, uint32_t m, const double* f, double* host_out) {
   k_gemv_t_partial<<<nblocks_, 256, 0, stream_>>>(V, n_, m, f, n_, dPartial_);
-  k_gemv_t_final<<<(m + 63) / 64, 64, 0, stream_>>>(dPartial_, nblocks_, m, dSmall_);
+  k_gemv_t_final<<<(m * 32 + 255) / 256, 256, 0, stream_>>>(dPartial_, nblocks_, m, dSmall_);
   cudaMemcpyAsync(host_out, dSmall_, sizeof(double) * m, cudaMemcpyDeviceToHost, stream_);
   cudaStreamSynchronize(stream_);
+}
+
+inline double Irlm::reorth_pass(uint32_t m, const double* h_host, const double* fin, double* vf) {
+  if (h_host) {
+    memcpy(hPinned_, h_host, sizeof(double) * m);
+    cudaMemcpyAsync(dH_, hPinned_, sizeof(double) * m, cudaMemcpyHostToDevice, stream_);
+  }
+  k_fused_reorth<48><<<nblocks256_, 256, 0, stream_>>>(dV_, n_, m, h_host ? dH_ : nullptr, fin,
+                                                        dF_, n_, dPartial2_);
+  k_gemv_t_final<<<((m + 1) * 32 + 255) / 256, 256, 0, stream_>>>(dPartial2_, nblocks256_, m + 1,
+                                                                   dSmall_);
+  cudaMemcpyAsync(hPinned_, dSmall_, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, stream_);
+  cudaStreamSynchronize(stream_);
+  memcpy(vf, hPinned_, sizeof(double) * m);
+  return sqrt(hPinned_[m]);
 }
 
 inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
@@ -377,11 +456,19 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
     gemv_t(col(i), 1, dW_, &Hii);
     H(i - 1, i) = H(i, i - 1);
     H(i, i) = Hii;
-    k_resid<<<grid1d(256), 256, 0, stream_>>>(dW_, restart ? nullptr : col(i - 1), H(i, i - 1),
-                                              col(i), Hii, dF_, n_);
-    beta = norm(dF_);
     const uint32_t i1 = i + 1;
-    gemv_t(dV_, i1, dF_, Vf.data());
+    if (fused_) {
+      // f = w - H(i,i-1) v_{i-1} - Hii v_i, V'f and ||f|| in one pass over V[:, :i+1]
+      std::vector<double> hc(i1, 0.0);
+      hc[i] = Hii;
+      if (!restart) hc[i - 1] = H(i, i - 1);
+      beta = reorth_pass(i1, hc.data(), dW_, Vf.data());
+    } else {
+      k_resid<<<grid1d(256), 256, 0, stream_>>>(dW_, restart ? nullptr : col(i - 1), H(i, i - 1),
+                                                col(i), Hii, dF_, n_);
+      beta = norm(dF_);
+      gemv_t(dV_, i1, dF_, Vf.data());
+    }
     auto maxabs = [&]() {
       double m = 0.0;
       for (uint32_t c = 0; c < i1; c++) m = std::max(m, fabs(Vf[c]));
@@ -395,13 +482,20 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
         beta = 0.0;
         break;
       }
-      cudaMemcpyAsync(dSmall_, Vf.data(), sizeof(double) * i1, cudaMemcpyHostToDevice, stream_);
-      k_gemv_n_sub<<<grid1d(256), 256, 0, stream_>>>(dV_, n_, i1, dSmall_, dF_, n_);
-      H(i - 1, i) += Vf[i - 1];
+      std::vector<double> hprev(Vf.begin(), Vf.begin() + i1);
+      H(i - 1, i) += hprev[i - 1];
       H(i, i - 1) = H(i - 1, i);
-      H(i, i) += Vf[i];
-      beta = norm(dF_);
-      gemv_t(dV_, i1, dF_, Vf.data());
+      H(i, i) += hprev[i];
+      if (fused_) {
+        beta = reorth_pass(i1, hprev.data(), dF_, Vf.data());
+      } else {
+        cudaMemcpyAsync(dSmall_, hprev.data(), sizeof(double) * i1, cudaMemcpyHostToDevice,
+                        stream_);
+        k_gemv_n_sub<<<grid1d(256), 256, 0, stream_>>>(dV_, n_, i1, dSmall_, dF_, n_);
+        cudaStreamSynchronize(stream_);
+        beta = norm(dF_);
+        gemv_t(dV_, i1, dF_, Vf.data());
+      }
       ortho_err = maxabs();
       count++;
     }
