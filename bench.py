@@ -259,7 +259,10 @@ def run_b200(a):
         res = op.pca(k, 2 * k + 1, 500, 1e-6)
         barrier()
         op_ms = op.op_times_ms()
-        solve = {"seconds": time.perf_counter() - t0, "nops": int(res["nops"]),
+        ph = op.pca_phase_seconds()
+        solve = {"seconds": time.perf_counter() - t0, "iterate_seconds": ph["iterate"],
+                 "eigenvector_assemble_seconds": ph["assemble"],
+                 "eigenvector_download_seconds": ph["download"], "nops": int(res["nops"]),
                  "nconv": int(res["nconv"]), "restarts": int(res["niter"]) - 1,
                  "median_op_ms": float(np.median(op_ms)) if op_ms.size else None,
                  "eigenvalue_1_over_p": float(res["values"][0] / p),

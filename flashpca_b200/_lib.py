@@ -47,6 +47,7 @@ SIGNATURES = {
     "fpb_pca": (_i, [_vp, _u32, _u32, _u32, _d, _vp, _vp, _c.POINTER(_u32), _c.POINTER(_u32),
                      _c.POINTER(_u32)]),
     "fpb_pca_op_times": (_u32, [_vp, _vp, _u32]),
+    "fpb_pca_phase_times": (None, [_vp, _vp]),
     "fpb_time_perform_op": (_i, [_vp, _vp, _vp, _u32, _c.POINTER(_c.c_float), _vp]),
     "fpb_launch_count": (_u64, [_vp]),
 }

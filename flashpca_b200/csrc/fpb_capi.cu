@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -124,6 +125,8 @@ struct fpb_handle {
   int nranks = 1, rank = 0;
   uint64_t launches = 0;
   std::vector<float> op_ms;
+  fpb::Irlm* solver = nullptr;  // Lanczos workspace, kept between fpb_pca calls
+  double pca_phase_s[4] = {0, 0, 0, 0};  // setup+iterate, eigenvectors, download, total
   std::string err;
 };
 
@@ -192,8 +195,15 @@ int alloc_common(fpb_handle* h, uint64_t n, uint64_t nsnps, int stand_method, in
   // main stream: everything ordered; side stream: the sparse missing-genotype
   // gathers (they only depend on the input vector, so they run ahead of the
   // contraction kernel and join before the finalize step)
-  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  FPB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  if (getenv("FPB_DEBUG_PRIO")) {  // debug: interleave the two streams' blocks on the SMs
+    int lo = 0, hi = 0;
+    FPB_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    FPB_CUDA(h, cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi));
+    FPB_CUDA(h, cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+  } else {
+    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  }
   FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->n = n;
@@ -475,7 +485,10 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
     const uint32_t splits = snp_major ? h->tsplits_s : h->tsplits_i;
     const uint32_t sps = snp_major ? h->sps_s : h->sps_i;
     dim3 grid((rows + fpb::kTmaRows - 1) / fpb::kTmaRows, splits);
-    fpb::k_imma_gemv_tma<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
+    // debug: FPB_DEBUG_SMEM_MIN requests only the bytes the ring needs, which lets
+    // blocks of other kernels share the SM (used to reproduce the co-residency race)
+    static const int smem_bytes = getenv("FPB_DEBUG_SMEM_MIN") ? fpb::kTmaSmemUsed : fpb::kTmaSmemBytes;
+    fpb::k_imma_gemv_tma<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, smem_bytes,
                            h->stream>>>(snp_major ? h->tm_s : h->tm_i, rows, h->d_slices, nstages,
                                         sps, h->d_part, h->part_stride);
     return splits;
@@ -725,6 +738,7 @@ void fpb_destroy(fpb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->side) cudaStreamSynchronize(h->side);
+  delete h->solver;
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_gs);
   cudaFree(h->d_gi);
@@ -921,10 +935,22 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
     evs.push_back(a);
     evs.push_back(b);
   };
-  fpb::Irlm solver(h->n, nev, ncv, h->stream, op);
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  const auto t0 = now();
+  if (h->solver && !h->solver->matches(h->n, nev, ncv)) {
+    delete h->solver;
+    h->solver = nullptr;
+  }
+  if (!h->solver) h->solver = new fpb::Irlm(h->n, nev, ncv, h->stream, op);
+  else h->solver->set_op(op);
+  fpb::Irlm& solver = *h->solver;
   fpb::IrlmResult res;
   solver.run(maxiter, tol, res);
   cudaStreamSynchronize(h->stream);
+  const auto t1 = now();
   for (size_t i = 0; i + 1 < evs.size(); i += 2) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
@@ -932,22 +958,41 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
     cudaEventDestroy(evs[i]);
     cudaEventDestroy(evs[i + 1]);
   }
-  if (op_rc) return 1;
-  if (!solver.error.empty()) FPB_FAIL(h, solver.error);
+  if (op_rc) {
+    solver.set_op(nullptr);
+    return 1;
+  }
+  if (!solver.error.empty()) {
+    solver.set_op(nullptr);
+    FPB_FAIL(h, solver.error);
+  }
   FPB_CUDA(h, cudaGetLastError());
   if (evals_out) memcpy(evals_out, res.evals.data(), sizeof(double) * nev);
+  auto t2 = t1, t3 = t1;
   if (evecs_out) {
     if (ensure_staging(h, 0, (size_t)h->n * nev)) return 1;
     solver.eigenvectors(h->d_out);
+    t2 = now();
     FPB_CUDA(h, cudaMemcpyAsync(evecs_out, h->d_out, sizeof(double) * h->n * nev,
                                 cudaMemcpyDeviceToHost, h->stream));
     FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    t3 = now();
   }
+  h->pca_phase_s[0] = secs(t0, t1);
+  h->pca_phase_s[1] = secs(t1, t2);
+  h->pca_phase_s[2] = secs(t2, t3);
+  h->pca_phase_s[3] = secs(t0, t3);
+  solver.set_op(nullptr);
   if (nconv_out) *nconv_out = res.nconv;
   if (nops_out) *nops_out = res.nops;
   if (niter_out) *niter_out = res.niter;
   FPB_CUDA(h, cudaGetLastError());
   return 0;
+}
+
+void fpb_pca_phase_times(const fpb_handle* h, double out_seconds[4]) {
+  if (!h || !out_seconds) return;
+  for (int i = 0; i < 4; i++) out_seconds[i] = h->pca_phase_s[i];
 }
 
 uint32_t fpb_pca_op_times(const fpb_handle* h, float* ms_out, uint32_t cap) {

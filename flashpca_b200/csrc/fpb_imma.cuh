@@ -472,6 +472,14 @@ k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* _
         }
       }
     }
+    // Release the stage.  The fence makes every lane's shared-memory reads of
+    // this stage complete before the arrive can be observed: without it ptxas
+    // schedules the SYNCS.ARRIVE right behind the *issue* of the stage's last
+    // LDS.128 (ahead of the IMMAs that consume it), and the producer's next TMA
+    // write into the slot can overtake that load when the LSU is congested
+    // (observed as per-warp corruption, profiles/r01_notes.md).
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __threadfence_block();
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 8 * (kTmaStages + slot));
     if ((it % kTmaFlushStages) == kTmaFlushStages - 1) {

@@ -18,6 +18,9 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <numeric>
@@ -330,6 +333,10 @@ class Irlm {
        std::function<void(const double*, double*)> op)
       : n_(n), nev_(nev), ncv_(ncv), stream_(stream), op_(std::move(op)) {}
   ~Irlm() { release(); }
+  void set_op(std::function<void(const double*, double*)> op) { op_ = std::move(op); }
+  bool matches(uint64_t n, uint32_t nev, uint32_t ncv) const {
+    return n == n_ && nev == nev_ && ncv == ncv_;
+  }
 
   // Runs init() + compute(maxit, tol).  On return d_V()/ritz vectors can be
   // combined with eigenvectors().
@@ -337,8 +344,14 @@ class Irlm {
   // evecs (N x nev, column-major, device) = V * ritz_vec, sorted like evals.
   void eigenvectors(double* d_out);
   std::string error;
+  double t_op = 0, t_hii = 0, t_reorth = 0, t_other = 0;  // host seconds by phase (trace)
+  uint32_t n_reorth = 0;
 
  private:
+  static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+  }
   void alloc();
   void release();
   void gemv_t(const double* V, uint32_t m, const double* f, double* host_out);
@@ -380,6 +393,14 @@ class Irlm {
 };
 
 inline void Irlm::alloc() {
+  if (dV_) {  // workspace kept from a previous solve on the same handle
+    cudaMemsetAsync(dV_, 0, sizeof(double) * n_ * ncv_, stream_);
+    H_.assign((size_t)ncv_ * ncv_, 0.0);
+    error.clear();
+    t_op = t_hii = t_reorth = t_other = 0;
+    n_reorth = 0;
+    return;
+  }
   nblocks_ = (uint32_t)((n_ + kRowsPerBlock - 1) / kRowsPerBlock);
   cudaMalloc(&dV_, sizeof(double) * n_ * ncv_);
   cudaMalloc(&dVs_, sizeof(double) * n_ * ncv_);
@@ -448,12 +469,17 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
       beta = norm(dF_);
       restart = true;
     }
+    double ta = now_s();
     k_axpby<<<grid1d(256), 256, 0, stream_>>>(1.0 / beta, dF_, 0.0, nullptr, col(i), n_);
     H(i, i - 1) = restart ? 0.0 : beta;
     op_(col(i), dW_);
     nops_++;
+    double tb = now_s();
     double Hii;
     gemv_t(col(i), 1, dW_, &Hii);
+    double tc = now_s();
+    t_op += tb - ta;
+    t_hii += tc - tb;
     H(i - 1, i) = H(i, i - 1);
     H(i, i) = Hii;
     const uint32_t i1 = i + 1;
@@ -498,7 +524,10 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
       }
       ortho_err = maxabs();
       count++;
+      n_reorth++;
     }
+    n_reorth++;
+    t_reorth += now_s() - tc;
   }
   beta_ = beta;
 }
@@ -588,6 +617,9 @@ inline void Irlm::run(uint32_t maxit, double tol, IrlmResult& res) {
     res.evals[i] = ritz_val_[order_[i]];
     res.conv[i] = conv[order_[i]];
   }
+  if (getenv("FPB_IRLM_TRACE"))
+    fprintf(stderr, "[irlm] ops %u: enqueue-op %.1f ms, wait-op+Hii %.1f ms, reorth %.1f ms (%u passes)\n",
+            nops_, t_op * 1e3, t_hii * 1e3, t_reorth * 1e3, n_reorth);
   res.nconv = nconv;
   res.nops = nops_;
   res.niter = it + 1;

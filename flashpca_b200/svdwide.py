@@ -157,6 +157,11 @@ class SVDWideOnline:
         return dict(values=evals, vectors=evecs, nconv=nconv.value, nops=nops.value,
                     niter=niter.value)
 
+    def pca_phase_seconds(self) -> dict:
+        buf = np.zeros(4)
+        self.lib.fpb_pca_phase_times(self.h, buf.ctypes.data)
+        return dict(iterate=buf[0], assemble=buf[1], download=buf[2], total=buf[3])
+
     def op_times_ms(self) -> np.ndarray:
         buf = np.zeros(4096, dtype=np.float32)
         m = self.lib.fpb_pca_op_times(self.h, buf.ctypes.data, buf.size)

@@ -143,6 +143,10 @@ int fpb_pca(fpb_handle *h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
 /* Per-op device timings of the last fpb_pca call, milliseconds (CUDA events on
  * the handle's stream); returns the number written (<= cap). */
 uint32_t fpb_pca_op_times(const fpb_handle *h, float *ms_out, uint32_t cap);
+/* Host wall-clock of the last fpb_pca call, seconds: [0] Lanczos iteration
+ * (setup included), [1] eigenvector assembly V*ritz, [2] download of the
+ * eigenvectors to the caller's buffer, [3] total. */
+void fpb_pca_phase_times(const fpb_handle *h, double out_seconds[4]);
 
 /* ---- measurement helpers (bench.py) --------------------------------------
  * Enqueue `reps` back-to-back device perform_op calls and return the mean

@@ -1,0 +1,118 @@
+"""GPU tests of the C++ front end (flashpca_b200/host -> `flashpca` binary) and
+of the multi-GPU path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, ROOT, load_fixture
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from flashpca_b200 import build
+    build.build_lib()
+    path = build.build_cli()
+    assert os.path.exists(path)
+    return path
+
+
+def _read_table(path, skip_header=True, first_numeric_col=2):
+    rows = open(path).read().splitlines()
+    hdr = rows[0].split("\t") if skip_header else None
+    body = rows[1:] if skip_header else rows
+    ids = [r.split("\t")[:first_numeric_col] for r in body]
+    vals = np.array([[float(v) for v in r.split("\t")[first_numeric_col:]] for r in body])
+    return hdr, ids, vals
+
+
+def test_cli_pca_outputs_match_dense(cli, tmp_path):
+    """HapMap3/test_pca.R:40-43 command line (BASELINE config 0): --ndim 10 --tol 1e-6
+    --outload --outmeansd --precision 20, outputs vs dense eigh, FID/IID order exact."""
+    stem = FIXTURES["hapmap3"]
+    out = subprocess.run([cli, "--bfile", stem, "--ndim", "10", "--tol", "1e-6", "--outload",
+                          "loadings.txt", "--outmeansd", "meansd.txt", "--precision", "20",
+                          "--notime", "-v"], cwd=tmp_path, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "PCA begin" in out.stdout and "PCA done" in out.stdout and "Goodbye!" in out.stdout
+    assert "blocksize: 14389 (" in out.stdout          # flashpca.cpp:690 log line
+    _, payload, n, p = load_fixture("hapmap3")
+    x, msd = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, 10)
+    ev = np.loadtxt(tmp_path / "eigenvalues.txt")
+    assert np.abs(ev / ref["d"] - 1).max() < 1e-6
+    pve = np.loadtxt(tmp_path / "pve.txt")
+    assert np.abs(pve / ref["pve"] - 1).max() < 1e-6
+    hdr, ids, u = _read_table(tmp_path / "eigenvectors.txt")
+    assert hdr == ["FID", "IID"] + ["U%d" % (i + 1) for i in range(10)]
+    fid, iid = O.read_fam_ids(stem + ".fam")
+    assert [r[0] for r in ids] == fid and [r[1] for r in ids] == iid   # bit-exact order
+    assert np.abs(O.sign_align(u, ref["U"]) - ref["U"]).max() < 5e-6    # tol 1e-6 solve
+    hdr, _, pcs = _read_table(tmp_path / "pcs.txt")
+    assert hdr[2] == "PC1"
+    assert np.abs(O.sign_align(pcs, ref["Px"]) - ref["Px"]).max() < 5e-6 * np.abs(ref["Px"]).max()
+    hdr, sid, ms = _read_table(tmp_path / "meansd.txt")
+    assert hdr == ["SNP", "RefAllele", "Mean", "SD"]
+    assert np.array_equal(ms, msd)                    # --precision 20 round-trips doubles
+    bim = [ln.split() for ln in open(stem + ".bim").read().splitlines()]
+    assert [r[0] for r in sid] == [b[1] for b in bim] and [r[1] for r in sid] == [b[4] for b in bim]
+    hdr, _, v = _read_table(tmp_path / "loadings.txt")
+    vref = O.dense_loadings(x, ref["U"], ref["d"], ref["div"])
+    assert np.abs(O.sign_align(v, vref) - vref).max() < 5e-6 * np.abs(vref).max()
+
+    # --check on the files just written (README.md:194-207): mse < 1e-8
+    chk = subprocess.run([cli, "--bfile", stem, "--check", "--outvec", "eigenvectors.txt",
+                          "--outval", "eigenvalues.txt", "--notime"], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=300)
+    assert chk.returncode == 0, chk.stdout + chk.stderr
+    mse = float(chk.stdout.split("Mean squared error: ")[1].split(",")[0])
+    assert mse < 1e-8
+
+    # --project with the saved loadings + mean/sd reproduces the PCs (HapMap3/test_pca.R:46-67)
+    prj = subprocess.run([cli, "--bfile", stem, "--project", "--inload", "loadings.txt",
+                          "--inmeansd", "meansd.txt", "--outproj", "proj.txt", "--notime",
+                          "--precision", "20"], cwd=tmp_path, capture_output=True, text=True,
+                         timeout=300)
+    assert prj.returncode == 0, prj.stdout + prj.stderr
+    _, _, proj = _read_table(tmp_path / "proj.txt")
+    assert np.abs(proj - pcs).max() < 1e-5 * np.abs(pcs).max()
+
+
+def test_cli_default_precision_and_errors(cli, tmp_path):
+    stem = FIXTURES["data_chr1"]
+    out = subprocess.run([cli, "--bfile", stem, "--ndim", "3", "--notime", "--suffix", ".tsv"],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = open(tmp_path / "eigenvalues.tsv").read().split()
+    assert len(lines) == 3 and all(len(v.replace(".", "").lstrip("0")) <= 7 for v in lines)
+    # max_dim guard (flashpca.cpp:623-633)
+    bad = subprocess.run([cli, "--bfile", stem, "--ndim", "500"], cwd=tmp_path,
+                         capture_output=True, text=True)
+    assert bad.returncode != 0 and "but only 478allowed" in bad.stderr
+    bad = subprocess.run([cli, "--bfile", stem, "--standx", "sd"], cwd=tmp_path,
+                         capture_output=True, text=True)
+    assert bad.returncode != 0 and "unknown standardization method" in bad.stderr
+    bad = subprocess.run([cli, "--bfile", "/nonexistent/x"], cwd=tmp_path, capture_output=True,
+                         text=True)
+    assert bad.returncode != 0 and "Error reading file" in bad.stderr
+    bad = subprocess.run([cli, "--bfile", stem, "--memory", "5", "--blocksize", "10"],
+                         cwd=tmp_path, capture_output=True, text=True)
+    assert bad.returncode != 0 and "cannot specify both --memory and --blocksize" in bad.stderr
+
+
+def test_nccl_sharded_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(ROOT, "tests", "_nccl_shard_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29617", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "NCCL_SHARD_OK" in out.stdout
