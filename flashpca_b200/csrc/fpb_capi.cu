@@ -102,8 +102,11 @@ struct fpb_handle {
   // tensor path
   bool use_imma = false;
   uint64_t nmissing = 0;
-  uint64_t *d_rowptr_s = nullptr, *d_rowptr_i = nullptr;
-  uint32_t *d_col_s = nullptr, *d_col_i = nullptr;
+  // column-blocked missing-genotype lists (fpb_imma.cuh): by SNP and by individual
+  uint64_t* d_rowptr_s = nullptr;  // staging only
+  uint64_t *d_seg_s = nullptr, *d_seg_i = nullptr;
+  uint16_t *d_col16_s = nullptr, *d_col16_i = nullptr;
+  uint32_t gtiles_s = 0, gtiles_i = 0;
   uint4* d_slices = nullptr;
   double* d_part = nullptr;
   double *d_a = nullptr, *d_b = nullptr, *d_corr = nullptr;
@@ -126,6 +129,9 @@ struct fpb_handle {
   uint64_t launches = 0;
   std::vector<float> op_ms;
   fpb::Irlm* solver = nullptr;  // Lanczos workspace, kept between fpb_pca calls
+  // fpb_time_perform_op: events bracketing the two contraction-kernel launches
+  bool time_gemv = false;
+  cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};
   double pca_phase_s[4] = {0, 0, 0, 0};  // setup+iterate, eigenvectors, download, total
   std::string err;
 };
@@ -255,6 +261,46 @@ void pick_splits(uint32_t rows, uint32_t nchunks, int sm_count, uint32_t* splits
   *splits = (nchunks + *cps - 1) / *cps;
 }
 
+// Column-blocked, row-sliced (SELL-32 per tile) lists of the missing entries of a
+// packed matrix G (rows x pitch); see fpb_imma.cuh.  Returns 2 when the padded
+// layout would be wasteful (very uneven rows): the caller then uses the generic path.
+int build_blocked_lists(fpb_handle* h, const uint8_t* G, uint64_t rows, uint64_t pitch,
+                        uint64_t veclen, const uint64_t* d_rowptr, uint64_t** d_blkoff,
+                        uint16_t** d_col16, uint32_t* ntiles_out) {
+  const uint32_t ntiles = (uint32_t)((veclen + fpb::kGatherTile - 1) / fpb::kGatherTile);
+  const uint32_t nblk = (uint32_t)((rows + 31) / 32);
+  const uint32_t gw = (uint32_t)((rows * 32 + 255) / 256);
+  uint32_t *d_col = nullptr, *d_counts = nullptr, *d_sizes = nullptr;
+  FPB_CUDA(h, cudaMalloc(&d_col, sizeof(uint32_t) * h->nmissing));
+  FPB_CUDA(h, cudaMalloc(&d_counts, sizeof(uint32_t) * (size_t)ntiles * rows));
+  FPB_CUDA(h, cudaMalloc(&d_sizes, sizeof(uint32_t) * (size_t)ntiles * nblk));
+  FPB_CUDA(h, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)ntiles * rows, h->stream));
+  fpb::k_fill_missing_csr<<<gw, 256, 0, h->stream>>>(G, rows, pitch, d_rowptr, d_col);
+  fpb::k_bcsr_count<<<gw, 256, 0, h->stream>>>(d_rowptr, d_col, rows, d_counts);
+  uint64_t nwarps = (uint64_t)ntiles * nblk;
+  fpb::k_sell_sizes<<<(uint32_t)((nwarps * 32 + 255) / 256), 256, 0, h->stream>>>(
+      d_counts, rows, nblk, ntiles, d_sizes);
+  uint64_t padded = 0;
+  if (build_rowptr(h, d_sizes, nwarps, d_blkoff, &padded)) return 1;
+  int rc = 0;
+  if (padded > 4 * h->nmissing + (64ull << 20)) {
+    rc = 2;  // padding would dominate
+  } else {
+    FPB_CUDA(h, cudaMalloc(d_col16, sizeof(uint16_t) * std::max<uint64_t>(padded, 1)));
+    FPB_CUDA(h, cudaMemsetAsync(*d_col16, 0x30, sizeof(uint16_t) * padded, h->stream));
+    fpb::k_sell_fill<<<gw, 256, 0, h->stream>>>(d_rowptr, d_col, rows, nblk, *d_blkoff, d_counts,
+                                                *d_col16);
+    h->launches += 4;
+    FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FPB_CUDA(h, cudaGetLastError());
+  }
+  cudaFree(d_col);
+  cudaFree(d_counts);
+  cudaFree(d_sizes);
+  *ntiles_out = ntiles;
+  return rc;
+}
+
 void pick_splits_tma(uint32_t rows, uint32_t nstages, int sm_count, uint32_t* splits,
                      uint32_t* sps) {
   uint32_t tiles = (rows + fpb::kTmaRows - 1) / fpb::kTmaRows;
@@ -351,22 +397,40 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
     h->launches++;
   }
   if (h->nmissing) {
-    FPB_CUDA(h, cudaMalloc(&h->d_col_s, sizeof(uint32_t) * h->nmissing));
-    FPB_CUDA(h, cudaMalloc(&h->d_col_i, sizeof(uint32_t) * h->nmissing));
-    fpb::k_fill_missing_csr<<<gs, 256, 0, h->stream>>>(h->d_gs, h->nsnps, h->pitch_s,
-                                                       h->d_rowptr_s, h->d_col_s);
-    uint32_t gi = (uint32_t)((h->n * 32 + 255) / 256);
-    fpb::k_row_missing<<<gi, 256, 0, h->stream>>>(h->d_gi, h->n, h->pitch_i, d_cnt);
-    uint64_t total_i = 0;
-    if (build_rowptr(h, d_cnt, h->n, &h->d_rowptr_i, &total_i)) return 1;
-    if (total_i != h->nmissing) FPB_FAIL(h, "internal error: transposed copy disagrees on missing count");
-    fpb::k_fill_missing_csr<<<gi, 256, 0, h->stream>>>(h->d_gi, h->n, h->pitch_i, h->d_rowptr_i,
-                                                       h->d_col_i);
-    h->launches += 3;
-  } else {
-    cudaFree(h->d_rowptr_s);
-    h->d_rowptr_s = nullptr;
+    // by SNP: rows = SNPs, gathered vector = x over individuals
+    int rc = build_blocked_lists(h, h->d_gs, h->nsnps, h->pitch_s, h->n, h->d_rowptr_s,
+                                 &h->d_seg_s, &h->d_col16_s, &h->gtiles_s);
+    if (rc == 1) return 1;
+    uint64_t* d_rowptr_i = nullptr;
+    if (rc == 0) {
+      // by individual: rows = individuals, gathered vector = corr over SNPs
+      uint32_t gi = (uint32_t)((h->n * 32 + 255) / 256);
+      fpb::k_row_missing<<<gi, 256, 0, h->stream>>>(h->d_gi, h->n, h->pitch_i, d_cnt);
+      h->launches++;
+      uint64_t total_i = 0;
+      if (build_rowptr(h, d_cnt, h->n, &d_rowptr_i, &total_i)) return 1;
+      if (total_i != h->nmissing)
+        FPB_FAIL(h, "internal error: transposed copy disagrees on missing count");
+      rc = build_blocked_lists(h, h->d_gi, h->n, h->pitch_i, h->nsnps, d_rowptr_i, &h->d_seg_i,
+                               &h->d_col16_i, &h->gtiles_i);
+      cudaFree(d_rowptr_i);
+      if (rc == 1) return 1;
+    }
+    if (rc == 2) {
+      // very uneven missingness: padded lists would dominate -> generic FP64 path
+      cudaFree(h->d_gi);
+      h->d_gi = nullptr;
+      cudaFree(h->d_rowptr_s);
+      h->d_rowptr_s = nullptr;
+      cudaFree(d_cnt);
+      h->use_imma = false;
+      FPB_CUDA(h, cudaMalloc(&h->d_coef, sizeof(double4) * h->nsnps));
+      FPB_CUDA(h, cudaMalloc(&h->d_c0, sizeof(double)));
+      return 0;
+    }
   }
+  cudaFree(h->d_rowptr_s);
+  h->d_rowptr_s = nullptr;
   cudaFree(d_cnt);
   h->nchunks_s = (uint32_t)((h->pitch_s + fpb::kChunkBytes - 1) / fpb::kChunkBytes);
   h->nchunks_i = (uint32_t)((h->pitch_i + fpb::kChunkBytes - 1) / fpb::kChunkBytes);
@@ -401,8 +465,11 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
   FPB_CUDA(h, cudaMalloc(&h->d_psum, sizeof(double) * kVecBlocks));
   FPB_CUDA(h, cudaMalloc(&h->d_sc, sizeof(fpb::VecScale) * 3));
   if (h->nmissing) {
-    FPB_CUDA(h, cudaMalloc(&h->d_mx, sizeof(double) * h->nsnps));
-    FPB_CUDA(h, cudaMalloc(&h->d_mc, sizeof(double) * h->n));
+    FPB_CUDA(h, cudaMalloc(&h->d_mx, sizeof(double) * h->nsnps * h->gtiles_s));
+    FPB_CUDA(h, cudaMalloc(&h->d_mc, sizeof(double) * h->n * h->gtiles_i));
+    FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_sell_gather,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fpb::kGatherSmem));
   }
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
   FPB_CUDA(h, cudaGetLastError());
@@ -480,6 +547,14 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
   fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(d_v, vlen, nwq, h->d_sc + slot,
                                                              h->d_slices);
   h->launches += 2;
+  if (h->time_gemv) cudaEventRecord(h->kev[snp_major ? 0 : 2], h->stream);
+  struct StopTimer {  // records the closing event when the launch has been enqueued
+    fpb_handle* h;
+    bool snp;
+    ~StopTimer() {
+      if (h->time_gemv) cudaEventRecord(h->kev[snp ? 1 : 3], h->stream);
+    }
+  } stop_timer{h, snp_major};
   if (h->use_tma) {
     const uint32_t nstages = snp_major ? h->nstages_s : h->nstages_i;
     const uint32_t splits = snp_major ? h->tsplits_s : h->tsplits_i;
@@ -507,11 +582,19 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
 // gather_launch() enqueues it; join_gather() makes the main stream wait for the
 // result before the finalize kernel.
 void fork_mark(fpb_handle* h) { cudaEventRecord(h->ev_fork, h->stream); }
-void gather_launch(fpb_handle* h, const uint64_t* rowptr, const uint32_t* colidx,
-                   const double* coef, uint64_t nrows, double* out) {
+void gather_launch(fpb_handle* h, bool by_snp, const double* vec) {
+  const uint64_t nrows = by_snp ? h->nsnps : h->n, veclen = by_snp ? h->n : h->nsnps;
+  const uint32_t ntiles = by_snp ? h->gtiles_s : h->gtiles_i;
   cudaStreamWaitEvent(h->side, h->ev_fork, 0);
-  uint32_t gb = (uint32_t)((nrows * 32 + 255) / 256);
-  fpb::k_csr_gather<<<gb, 256, 0, h->side>>>(rowptr, colidx, coef, nrows, out);
+  // about two full waves of 2 CTAs per SM (rounded down so the last wave is not a sliver)
+  const uint32_t nblk = (uint32_t)((nrows + 31) / 32);
+  uint32_t chunks = std::max<uint32_t>(1, (4u * h->sm_count) / ntiles);
+  uint32_t blocks_per_cta = (nblk + chunks - 1) / chunks;
+  chunks = (nblk + blocks_per_cta - 1) / blocks_per_cta;
+  dim3 grid(ntiles, chunks);
+  fpb::k_sell_gather<<<grid, fpb::kGatherThreads, fpb::kGatherSmem, h->side>>>(
+      by_snp ? h->d_seg_s : h->d_seg_i, by_snp ? h->d_col16_s : h->d_col16_i, vec, veclen, nrows,
+      nblk, blocks_per_cta, by_snp ? h->d_mx : h->d_mc);
   cudaEventRecord(h->ev_join, h->side);
   h->launches++;
 }
@@ -521,17 +604,17 @@ void join_gather(fpb_handle* h) { cudaStreamWaitEvent(h->stream, h->ev_join, 0);
 void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_half) {
   const bool gfirst = true;
   if (h->nmissing) fork_mark(h);
-  if (h->nmissing && gfirst) gather_launch(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
+  if (h->nmissing && gfirst) gather_launch(h, true, d_x);
   vec_prepare(h, d_x, h->n, 0);
   const uint32_t nsplits = imma_contract(h, true, d_x, h->n, 0);
   if (h->nmissing) {
-    if (!gfirst) gather_launch(h, h->d_rowptr_s, h->d_col_s, d_x, h->nsnps, h->d_mx);
+    if (!gfirst) gather_launch(h, true, d_x);
     join_gather(h);
   }
   uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
   fpb::k_finalize_crossprod<<<gb, 256, 0, h->stream>>>(
       h->d_part, nsplits, h->part_stride, (uint32_t)h->nsnps, h->d_sc + 0, h->d_scale,
-      h->nmissing ? h->d_mx : nullptr, d_t, second_half ? h->d_a : nullptr, h->d_b, h->d_corr);
+      h->nmissing ? h->d_mx : nullptr, h->gtiles_s, d_t, second_half ? h->d_a : nullptr, h->d_b, h->d_corr);
   h->launches++;
 }
 
@@ -539,18 +622,19 @@ void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_h
 void imma_prod_tail(fpb_handle* h, double* d_y) {
   const bool gfirst = true;
   if (h->nmissing) fork_mark(h);
-  if (h->nmissing && gfirst) gather_launch(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
+  if (h->nmissing && gfirst) gather_launch(h, false, h->d_corr);
   vec_prepare(h, h->d_a, h->nsnps, 1);
   vec_prepare(h, h->d_b, h->nsnps, 2);
   const uint32_t nsplits = imma_contract(h, false, h->d_a, h->nsnps, 1);
   if (h->nmissing) {
-    if (!gfirst) gather_launch(h, h->d_rowptr_i, h->d_col_i, h->d_corr, h->n, h->d_mc);
+    if (!gfirst) gather_launch(h, false, h->d_corr);
     join_gather(h);
   }
   uint32_t gb = (uint32_t)((h->n + 255) / 256);
   fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, nsplits, h->part_stride, h->n,
                                                   h->d_sc + 1, h->d_sc + 2,
-                                                  h->nmissing ? h->d_mc : nullptr, d_y);
+                                                  h->nmissing ? h->d_mc : nullptr, h->gtiles_i,
+                                                  d_y);
   h->launches++;
 }
 
@@ -739,14 +823,17 @@ void fpb_destroy(fpb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->side) cudaStreamSynchronize(h->side);
   delete h->solver;
+  for (int i = 0; i < 4; i++)
+    if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_gs);
   cudaFree(h->d_gi);
   cudaFree(h->d_scale);
   cudaFree(h->d_rowptr_s);
-  cudaFree(h->d_rowptr_i);
-  cudaFree(h->d_col_s);
-  cudaFree(h->d_col_i);
+  cudaFree(h->d_seg_s);
+  cudaFree(h->d_seg_i);
+  cudaFree(h->d_col16_s);
+  cudaFree(h->d_col16_i);
   cudaFree(h->d_slices);
   cudaFree(h->d_part);
   cudaFree(h->d_a);
@@ -942,6 +1029,8 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
   const auto t0 = now();
   if (h->solver && !h->solver->matches(h->n, nev, ncv)) {
     delete h->solver;
+  for (int i = 0; i < 4; i++)
+    if (h->kev[i]) cudaEventDestroy(h->kev[i]);
     h->solver = nullptr;
   }
   if (!h->solver) h->solver = new fpb::Irlm(h->n, nev, ncv, h->stream, op);
@@ -1017,16 +1106,25 @@ int fpb_time_perform_op(fpb_handle* h, const double* d_x, double* d_y, uint32_t 
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_per_op_out) *ms_per_op_out = ms / reps;
   if (ms_kernels_out) {
-    // one more op with events around each dominant kernel
+    // one more op with events around each half, and around each contraction kernel
+    for (int i = 0; i < 4; i++)
+      if (!h->kev[i]) cudaEventCreate(&h->kev[i]);
+    h->time_gemv = h->use_imma;
     cudaEventRecord(e0, h->stream);
     launch_crossprod(h, d_x, h->d_t);
     cudaEventRecord(e1, h->stream);
     cudaEventRecord(e2, h->stream);
     launch_prod(h, h->d_t, d_y);
     cudaEventRecord(e3, h->stream);
+    h->time_gemv = false;
     FPB_CUDA(h, cudaEventSynchronize(e3));
     cudaEventElapsedTime(&ms_kernels_out[0], e0, e1);
     cudaEventElapsedTime(&ms_kernels_out[1], e2, e3);
+    ms_kernels_out[2] = ms_kernels_out[3] = 0.f;
+    if (h->use_imma) {
+      cudaEventElapsedTime(&ms_kernels_out[2], h->kev[0], h->kev[1]);
+      cudaEventElapsedTime(&ms_kernels_out[3], h->kev[2], h->kev[3]);
+    }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   FPB_CUDA(h, cudaGetLastError());

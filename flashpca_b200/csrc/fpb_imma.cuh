@@ -514,45 +514,153 @@ k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* _
 }
 
 // ---------------------------------------------------------------------------
-// Sparse missing-genotype sums: one warp per row of a CSR list,
-//   out[r] = sum over the row's column indices of coef[col]   (fixed order).
-// Runs on the handle's side stream, concurrently with k_imma_gemv.
+// Sparse missing-genotype sums  out[r] = sum_{c in row r} vec[c].
+//
+// A plain CSR gather is bound by L2 sector traffic (every 8-byte read of `vec`
+// pulls a 32-byte sector: 0.28 ms per pass at 7.5e7 entries).  The lists are
+// therefore stored column-blocked and row-sliced (SELL-32 per tile):
+//   * the gathered vector is cut into tiles of kGatherTile elements that fit in
+//     shared memory;
+//   * inside a tile, rows are grouped in blocks of 32; a block stores its
+//     entries interleaved, slot (i, lane) = i-th entry of row 32*blk + lane, as
+//     16-bit in-tile column offsets, padded to the longest row of the block
+//     with an index that points at a zero in shared memory.
+// A CTA loads one tile of the vector into shared memory; a warp walks a block
+// with one coalesced 64-byte load, one LDS and one DADD per 32 entries, each
+// lane owning one row's sum (no shuffles, no atomics).  Per-tile partial sums
+// are added in tile order by the finalize kernels => bit-reproducible.
 // ---------------------------------------------------------------------------
+constexpr int kGatherTile = 12288;                        // 96 KB of doubles: 2 CTAs per SM
+constexpr int kGatherPad = 64;                            // zero slots behind the tile
+constexpr int kGatherSentinel = 0x3030;                   // = memset byte 0x30 twice, inside the pad
+constexpr int kGatherSmem = (kGatherTile + kGatherPad) * 8;
+constexpr int kGatherThreads = 512;
+static_assert(kGatherSentinel >= kGatherTile && kGatherSentinel < kGatherTile + kGatherPad,
+              "padding sentinel must point into the zero pad");
+
+// counts[t * nrows + r] = entries of row r whose column falls in tile t (one warp per row)
 __global__ void __launch_bounds__(256)
-k_csr_gather(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
-             const double* __restrict__ coef, uint64_t nrows, double* __restrict__ out) {
+k_bcsr_count(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
+             uint64_t nrows, uint32_t* __restrict__ counts) {
   uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (r >= nrows) return;
-  uint64_t b = rowptr[r], e = rowptr[r + 1];
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  uint64_t k = b + lane;
-  for (; k + 96 < e; k += 128) {
-    uint32_t c0 = colidx[k], c1 = colidx[k + 32], c2 = colidx[k + 64], c3 = colidx[k + 96];
-    s0 += coef[c0];
-    s1 += coef[c1];
-    s2 += coef[c2];
-    s3 += coef[c3];
+  for (uint64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32)
+    atomicAdd(counts + (uint64_t)(colidx[k] / kGatherTile) * nrows + r, 1u);
+}
+
+// sizes[t * nblk + b] = 32 * (longest row of block b in tile t); one warp per (t, b)
+__global__ void __launch_bounds__(256)
+k_sell_sizes(const uint32_t* __restrict__ counts, uint64_t nrows, uint32_t nblk, uint32_t ntiles,
+             uint32_t* __restrict__ sizes) {
+  uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= (uint64_t)ntiles * nblk) return;
+  uint32_t t = (uint32_t)(w / nblk), b = (uint32_t)(w % nblk);
+  uint64_t r = (uint64_t)b * 32 + lane;
+  uint32_t c = r < nrows ? counts[(uint64_t)t * nrows + r] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+  if (lane == 0) sizes[w] = c * 32u;
+}
+
+// scatter the CSR entries into their SELL-32 slots (col16 pre-filled with the sentinel)
+__global__ void __launch_bounds__(256)
+k_sell_fill(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
+            uint64_t nrows, uint32_t nblk, const uint64_t* __restrict__ blkoff,
+            const uint32_t* __restrict__ counts, uint16_t* __restrict__ col16) {
+  uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  const uint64_t b = rowptr[r], e = rowptr[r + 1];
+  for (uint64_t k = b + lane; k < e; k += 32) {
+    uint32_t c = colidx[k], t = c / kGatherTile;
+    uint64_t before = 0;  // entries of this row in earlier tiles (columns ascend within a row)
+    for (uint32_t tt = 0; tt < t; tt++) before += counts[(uint64_t)tt * nrows + r];
+    const uint64_t rank = k - b - before;
+    col16[blkoff[(uint64_t)t * nblk + (r >> 5)] + rank * 32 + (r & 31)] =
+        (uint16_t)(c - t * kGatherTile);
   }
-  for (; k < e; k += 32) s0 += coef[colidx[k]];
-  double s = warp_sum((s0 + s1) + (s2 + s3));
-  if (lane == 0) out[r] = s;
+}
+
+// grid (ntiles, chunks of row blocks); partial[t * nrows + r] = sum over tile t of row r
+__global__ void __launch_bounds__(kGatherThreads, 2)
+k_sell_gather(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ col16,
+              const double* __restrict__ vec, uint64_t veclen, uint64_t nrows, uint32_t nblk,
+              uint32_t blocks_per_cta, double* __restrict__ partial) {
+  extern __shared__ double xs[];
+  const uint32_t t = blockIdx.x;
+  const uint64_t base = (uint64_t)t * kGatherTile;
+  {
+    constexpr int PER = kGatherTile / kGatherThreads;  // 24 loads per thread, issued together
+    double tmp[PER];
+#pragma unroll
+    for (int m = 0; m < PER; m++) {
+      const uint32_t i = threadIdx.x + m * kGatherThreads;
+      tmp[m] = (base + i < veclen) ? vec[base + i] : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < PER; m++) xs[threadIdx.x + m * kGatherThreads] = tmp[m];
+    if (threadIdx.x < kGatherPad) xs[kGatherTile + threadIdx.x] = 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b0 = blockIdx.y * blocks_per_cta, b1 = min(nblk, b0 + blocks_per_cta);
+  const uint64_t* bo = blkoff + (uint64_t)t * nblk;
+  double* out = partial + (uint64_t)t * nrows;
+  constexpr int NW = kGatherThreads / 32;
+  uint32_t b = b0 + warp;
+  uint64_t o = 0, onext = 0;
+  if (b < b1) {
+    o = bo[b];
+    onext = bo[b + 1];
+  }
+  for (; b < b1; b += NW) {
+    const uint32_t width = (uint32_t)((onext - o) >> 5);
+    const uint16_t* cp = col16 + o + lane;
+    // pointers of the warp's next block, fetched while this one is processed
+    uint64_t o2 = 0, o2next = 0;
+    if (b + NW < b1) {
+      o2 = bo[b + NW];
+      o2next = bo[b + NW + 1];
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (uint32_t i = 0; i < width; i += 16) {
+      uint16_t c[16];
+#pragma unroll
+      for (int m = 0; m < 16; m++)  // 16 independent coalesced loads in flight
+        c[m] = (i + m < width) ? cp[(i + m) * 32] : (uint16_t)kGatherSentinel;
+#pragma unroll
+      for (int m = 0; m < 16; m += 4) {
+        s0 += xs[c[m]];
+        s1 += xs[c[m + 1]];
+        s2 += xs[c[m + 2]];
+        s3 += xs[c[m + 3]];
+      }
+    }
+    const uint64_t r = (uint64_t)b * 32 + lane;
+    if (r < nrows) out[r] = (s0 + s1) + (s2 + s3);
+    o = o2;
+    onext = o2next;
+  }
 }
 
 // Finalise X'x for SNP j:
 //   E_j = delta * sum_splits part[s][j];   t_j = [(E_j - 3 Mx_j) - mu_j (Sx - Mx_j)] * inv_sd_j
 // t_out (optional) receives t_j; a_out (optional) receives a_j = t_j * inv_sd_j,
 // b_j = mu_j a_j, corr_j = b_j - 3 a_j (inputs of the second half of perform_op).
-// mx may be null (no missing genotypes at all).
+// mxv: mx_tiles x nsnps per-tile partial sums of Mx (null when nothing is missing).
 __global__ void __launch_bounds__(256)
 k_finalize_crossprod(const double* __restrict__ part, uint32_t nsplits, uint64_t stride,
                      uint32_t nsnps, const VecScale* __restrict__ sc,
                      const double2* __restrict__ scale, const double* __restrict__ mxv,
-                     double* __restrict__ t_out, double* __restrict__ a_out,
+                     uint32_t mx_tiles, double* __restrict__ t_out, double* __restrict__ a_out,
                      double* __restrict__ b_out, double* __restrict__ corr_out) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nsnps) return;
-  double mx = mxv ? mxv[j] : 0.0;
+  double mx = 0.0;
+  if (mxv)
+    for (uint32_t tt = 0; tt < mx_tiles; tt++) mx += mxv[(uint64_t)tt * nsnps + j];
   double e = 0.0;
   for (uint32_t s = 0; s < nsplits; s++) e += part[(uint64_t)s * stride + j];
   e *= sc->delta;
@@ -588,12 +696,15 @@ __global__ void k_prod_inputs(const double* __restrict__ v, const double2* __res
 __global__ void __launch_bounds__(256)
 k_finalize_prod(const double* __restrict__ part, uint32_t nsplits, uint64_t stride, uint64_t n,
                 const VecScale* __restrict__ sc_a, const VecScale* __restrict__ sc_b,
-                const double* __restrict__ mcv, double* __restrict__ y) {
+                const double* __restrict__ mcv, uint32_t mc_tiles, double* __restrict__ y) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double f = 0.0;
   for (uint32_t s = 0; s < nsplits; s++) f += part[(uint64_t)s * stride + i];
-  y[i] = f * sc_a->delta - sc_b->sum + (mcv ? mcv[i] : 0.0);
+  double mc = 0.0;
+  if (mcv)
+    for (uint32_t tt = 0; tt < mc_tiles; tt++) mc += mcv[(uint64_t)tt * n + i];
+  y[i] = f * sc_a->delta - sc_b->sum + mc;
 }
 
 }  // namespace fpb

@@ -150,8 +150,11 @@ void fpb_pca_phase_times(const fpb_handle *h, double out_seconds[4]);
 
 /* ---- measurement helpers (bench.py) --------------------------------------
  * Enqueue `reps` back-to-back device perform_op calls and return the mean
- * milliseconds per call (CUDA events on fpb_stream(h)); ms_kernels_out[0..1]
- * (may be NULL) receive the mean crossprod / prod kernel times. */
+ * milliseconds per call (CUDA events on fpb_stream(h)).  ms_kernels_out (may be
+ * NULL, else 4 floats) receives, from one further op: [0] the X'x half, [1] the
+ * X t half (each with its small kernels), [2], [3] the contraction kernel of
+ * each half alone (events recorded immediately around its launch; 0 on the
+ * generic FP64 path). */
 int fpb_time_perform_op(fpb_handle *h, const double *d_x, double *d_y, uint32_t reps,
                         float *ms_per_op_out, float *ms_kernels_out);
 /* Number of kernels this library has launched on the handle so far. */
