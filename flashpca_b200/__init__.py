@@ -9,11 +9,11 @@ and bench.py; it binds the C ABI with ctypes and has no CPU fallback.
 """
 from .data import Data
 from .randompca import RandomPCA
-from .svdwide import SVDWideOnline
+from .svdwide import SVDWide, SVDWideOnline
 
 STANDARDISE_BINOM = 2   # util.h:36
 STANDARDISE_BINOM2 = 3  # util.h:37
 DIVISOR_NONE, DIVISOR_N1, DIVISOR_P = 0, 1, 2  # randompca.h:50-52
 
-__all__ = ["Data", "SVDWideOnline", "RandomPCA", "STANDARDISE_BINOM", "STANDARDISE_BINOM2",
+__all__ = ["Data", "SVDWide", "SVDWideOnline", "RandomPCA", "STANDARDISE_BINOM", "STANDARDISE_BINOM2",
            "DIVISOR_NONE", "DIVISOR_N1", "DIVISOR_P"]

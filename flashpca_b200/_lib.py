@@ -23,6 +23,8 @@ SIGNATURES = {
     "fpb_create_from_file": (_i, [_c.POINTER(_vp), _c.c_char_p, _u64, _u64, _u64, _i, _vp, _i]),
     "fpb_create_synthetic": (_i, [_c.POINTER(_vp), _u64, _u64, _u64, _vp, _vp, _u32, _u32, _u64,
                                   _i, _i]),
+    "fpb_create_dense": (_i, [_c.POINTER(_vp), _vp, _u64, _u64, _i, _i]),
+    "fpb_get_dense": (_i, [_vp, _vp]),
     "fpb_destroy": (None, [_vp]),
     "fpb_rows": (_u64, [_vp]),
     "fpb_cols": (_u64, [_vp]),

@@ -27,6 +27,7 @@
 
 #include <stdlib.h>
 
+#include "fpb_dense.cuh"
 #include "fpb_imma.cuh"
 #include "fpb_irlm.cuh"
 #include "fpb_kernels.cuh"
@@ -99,6 +100,10 @@ struct fpb_handle {
   double4* d_coef = nullptr;
   double* d_c0 = nullptr;
   Tiling tl;
+  // in-memory matrix path (fpb_create_dense): N x P doubles, already standardised
+  bool dense = false;
+  double* d_X = nullptr;
+  uint32_t dense_splits = 1, dense_cps = 1;
   // tensor path
   bool use_imma = false;
   uint64_t nmissing = 0;
@@ -638,15 +643,31 @@ void imma_prod_tail(fpb_handle* h, double* d_y) {
   h->launches++;
 }
 
+void dense_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
+  fpb::k_dense_gemv_t<<<(uint32_t)h->nsnps, 256, 0, h->stream>>>(h->d_X, h->n, d_x, d_t);
+  h->launches++;
+}
+void dense_prod(fpb_handle* h, const double* d_v, double* d_y) {
+  dim3 grid((uint32_t)((h->n + 255) / 256), h->dense_splits);
+  fpb::k_dense_gemv_n<<<grid, 256, 0, h->stream>>>(h->d_X, h->n, (uint32_t)h->nsnps,
+                                                    h->dense_cps, d_v, h->d_part);
+  fpb::k_sum_splits<<<(uint32_t)((h->n + 255) / 256), 256, 0, h->stream>>>(
+      h->d_part, h->dense_splits, h->n, d_y);
+  h->launches += 2;
+}
+
 // t (nsnps) = X' x
 void launch_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
-  if (h->use_imma) imma_crossprod(h, d_x, d_t, false);
+  if (h->dense) dense_crossprod(h, d_x, d_t);
+  else if (h->use_imma) imma_crossprod(h, d_x, d_t, false);
   else generic_crossprod(h, d_x, d_t);
 }
 
 // y (N) = X v
 void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
-  if (h->use_imma) {
+  if (h->dense) {
+    dense_prod(h, d_v, d_y);
+  } else if (h->use_imma) {
     uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
     fpb::k_prod_inputs<<<gb, 256, 0, h->stream>>>(d_v, h->d_scale, (uint32_t)h->nsnps, h->d_a,
                                                   h->d_b, h->d_corr);
@@ -659,7 +680,10 @@ void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
 
 // y (N) = X X' x
 void launch_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
-  if (h->use_imma) {
+  if (h->dense) {  // y = mat * (mat' x), svdwide.cpp:10
+    dense_crossprod(h, d_x, h->d_t);
+    dense_prod(h, h->d_t, d_y);
+  } else if (h->use_imma) {
     imma_crossprod(h, d_x, nullptr, true);
     imma_prod_tail(h, d_y);
   } else {
@@ -817,6 +841,66 @@ int fpb_create_synthetic(fpb_handle** out, uint64_t n, uint64_t nsnps, uint64_t 
   return 0;
 }
 
+int fpb_create_dense(fpb_handle** out, const double* x_host, uint64_t n, uint64_t p,
+                     int stand_method, int device) {
+  if (!out || !x_host) FPB_FAIL((fpb_handle*)nullptr, "null argument");
+  *out = nullptr;
+  if (stand_method < 0 || stand_method > 4)
+    FPB_FAIL((fpb_handle*)nullptr, "unknown standardization method");  // util.cpp:179
+  if (n == 0 || p == 0 || p > 0xFFFFFFF0ull)
+    FPB_FAIL((fpb_handle*)nullptr, "empty genotype matrix (N == 0 or nsnps == 0)");
+  fpb_handle* h = new fpb_handle();
+  int rc = [&]() -> int {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      FPB_FAIL(h, std::string("no usable CUDA device (flashpca_b200 has no CPU fallback): ") +
+                      cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) FPB_FAIL(h, "invalid CUDA device ordinal");
+    h->device = device;
+    FPB_CUDA(h, cudaSetDevice(device));
+    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->dense = true;
+    h->n = n;
+    h->nsnps = p;
+    h->stand_method = stand_method;
+    FPB_CUDA(h, cudaMalloc(&h->d_X, sizeof(double) * n * p));
+    FPB_CUDA(h, cudaMalloc(&h->d_meansd, sizeof(double) * 2 * p));
+    FPB_CUDA(h, cudaMalloc(&h->d_t, sizeof(double) * p));
+    double* d_colsq = nullptr;
+    FPB_CUDA(h, cudaMalloc(&d_colsq, sizeof(double) * p));
+    FPB_CUDA(h, cudaMemcpyAsync(h->d_X, x_host, sizeof(double) * n * p, cudaMemcpyHostToDevice,
+                                h->stream));
+    fpb::k_dense_standardise<<<(uint32_t)p, 256, 0, h->stream>>>(h->d_X, n, (uint32_t)p,
+                                                                 stand_method, h->d_meansd,
+                                                                 d_colsq);
+    h->launches++;
+    std::vector<double> sq(p);
+    FPB_CUDA(h, cudaMemcpyAsync(sq.data(), d_colsq, sizeof(double) * p, cudaMemcpyDeviceToHost,
+                                h->stream));
+    FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FPB_CUDA(h, cudaGetLastError());
+    cudaFree(d_colsq);
+    double tr = 0.0;
+    for (double v : sq) tr += v;
+    h->trace = tr;
+    // column splits of the X t product so that small-N matrices still fill the GPU
+    uint64_t rowblocks = (n + 255) / 256;
+    uint64_t splits = std::max<uint64_t>(1, std::min<uint64_t>(p / 64 + 1, (592 + rowblocks - 1) / rowblocks));
+    h->dense_cps = (uint32_t)((p + splits - 1) / splits);
+    h->dense_splits = (uint32_t)((p + h->dense_cps - 1) / h->dense_cps);
+    FPB_CUDA(h, cudaMalloc(&h->d_part, sizeof(double) * n * h->dense_splits));
+    return 0;
+  }();
+  if (rc) {
+    g_err = h->err;
+    fpb_destroy(h);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
 void fpb_destroy(fpb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
@@ -826,6 +910,7 @@ void fpb_destroy(fpb_handle* h) {
   for (int i = 0; i < 4; i++)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->d_X);
   cudaFree(h->d_gs);
   cudaFree(h->d_gi);
   cudaFree(h->d_scale);
@@ -881,6 +966,7 @@ int fpb_get_trace(fpb_handle* h, double* out_trace) {
 
 int fpb_get_bed(fpb_handle* h, unsigned char* out_payload) {
   if (!h || !out_payload) FPB_FAIL(h, "null argument");
+  if (h->dense) FPB_FAIL(h, "fpb_get_bed: the handle holds a dense matrix, not a bed");
   FPB_CUDA(h, cudaSetDevice(h->device));
   uint8_t* d_tmp = nullptr;
   uint64_t total = h->nsnps * h->np;
@@ -978,6 +1064,16 @@ int fpb_comm_unique_id(unsigned char id_out[128]) {
   int rc = g_nccl.GetUniqueId(&id);
   if (rc != 0) FPB_FAIL((fpb_handle*)nullptr, "ncclGetUniqueId failed");
   memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+int fpb_get_dense(fpb_handle* h, double* out_x) {
+  if (!h || !out_x) FPB_FAIL(h, "null argument");
+  if (!h->dense) FPB_FAIL(h, "fpb_get_dense: the handle holds a bed, not a dense matrix");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  FPB_CUDA(h, cudaMemcpyAsync(out_x, h->d_X, sizeof(double) * h->n * h->nsnps,
+                              cudaMemcpyDeviceToHost, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -363,20 +363,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// The genotype tiles are read exactly once per launch (evict-first in L2); the
+// slice blocks are re-read by every row tile of the grid (evict-last).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int x, int y,
-                                            uint32_t bar) {
+                                            uint32_t bar, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(tmap), "r"(x), "r"(y), "r"(bar)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(tmap), "r"(x), "r"(y), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes,
-                                          uint32_t bar) {
+                                          uint32_t bar, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
 
@@ -411,15 +423,17 @@ k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* _
     // ------------------------------ producer ------------------------------
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
       for (uint32_t it = 0; it < nst; it++) {
         const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
         const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTmaStages + slot);
         if (round > 0) mbar_wait(empty, (round - 1) & 1);
         const uint32_t dst = base + slot * kTmaStageBytes;
         mbar_expect_tx(full, kTmaStageBytes);
-        tma_load_2d(dst, &tmap, (int)((s_begin + it) * kTmaStageCols), (int)row0, full);
-        bulk_load(dst + kTmaTileBytes,
-                  S + (uint64_t)(s_begin + it) * (kTmaSliceBytes / 16), kTmaSliceBytes, full);
+        tma_load_2d(dst, &tmap, (int)((s_begin + it) * kTmaStageCols), (int)row0, full,
+                    pol_stream);
+        bulk_load(dst + kTmaTileBytes, S + (uint64_t)(s_begin + it) * (kTmaSliceBytes / 16),
+                  kTmaSliceBytes, full, pol_keep);
       }
     }
     return;

@@ -102,6 +102,42 @@ void Data::prepare() {
               << " bytes, " << N << " samples, " << nsnps << " SNPs." << std::endl;
 }
 
+// data.cpp:339-406: the whole bed as doubles (minor-allele dosage, decode_plink
+// data.cpp:65-126), missing genotypes imputed to the per-SNP average of the
+// non-missing ones.  Only the non-transposed form is used by the PCA path.
+void Data::read_bed(bool transpose) {
+  if (transpose) throw std::runtime_error("read_bed(transpose=true) is not used by the PCA path");
+  std::ifstream in(geno_filename, std::ios::in | std::ios::binary);
+  if (!in) throw std::runtime_error(std::string("[Data::read_bed] Error reading file ") + geno_filename);
+  in.seekg(3, std::ifstream::beg);
+  X = Matrix(N, nsnps);
+  std::vector<unsigned char> tmp(np);
+  for (unsigned int j = 0; j < nsnps; j++) {
+    in.read((char*)tmp.data(), np);
+    double avg = 0;
+    unsigned int ngood = 0;
+    double* col = X.col(j);
+    for (unsigned int i = 0; i < N; i++) {
+      unsigned char g = (tmp[i >> 2] >> (2 * (i & 3))) & 3;
+      // 00 -> 2, 10 -> 1, 11 -> 0, 01 -> missing
+      if (g == 1) {
+        col[i] = -1.0;
+      } else {
+        double s = (double)(!(g & 1) + !(g >> 1));
+        col[i] = s;
+        avg += s;
+        ngood++;
+      }
+    }
+    avg /= ngood;
+    for (unsigned int i = 0; i < N; i++)
+      if (col[i] < 0) col[i] = avg;
+  }
+  if (verbose)
+    std::cout << timestamp() << "Loaded genotypes: " << N << " samples, " << nsnps << " SNPs"
+              << std::endl;
+}
+
 Matrix read_MAF(const char* filename, const std::vector<std::string>& snp_ids, bool verbose) {
   std::ifstream in(filename, std::ios::in);
   if (!in)

@@ -12,6 +12,7 @@ namespace flashpca {
 
 class Data {
  public:
+  Matrix X;         // N x nsnps dosages, only filled by read_bed (--batch)
   Matrix X_meansd;  // nsnps x 2 (mean, sd): data.cpp:198,290-291
   unsigned int N = 0, nsnps = 0;
   unsigned long long len = 0, np = 0;
@@ -27,6 +28,7 @@ class Data {
   void read_plink_fam(const char* filename);                    // data.cpp:639-672
   void get_size();                                              // data.cpp:150-176
   void prepare();                                               // data.cpp:179-206
+  void read_bed(bool transpose);                                // data.cpp:339-406
 };
 
 // data.cpp:419-496: plink .frq (CHR SNP A1 A2 MAF NCHROBS), SNP ids must match the bim.

@@ -3,8 +3,8 @@
 // messages and output files follow upstream flashpca.cpp:40-892; Boost
 // program_options is replaced by a small parser with the same surface
 // (--opt value, --opt=value, and the short forms -p -m -b -n -d -s -v -f -c).
-// SCCA / UCCA / --batch are outside this build's scope and are rejected with a
-// clear message.
+// --batch (all genotypes as doubles, the in-memory matrix path) is supported;
+// SCCA / UCCA are outside this build's scope and are rejected with a clear message.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -43,7 +43,7 @@ const OptSpec kOptions[] = {
     {"scca", 0, false, "perform sparse canonical correlation analysis (SCCA) [not in this build]"},
     {"ucca", 0, false, "perform per-SNP canonical correlation analysis [not in this build]"},
     {"project", 'p', false, "project new samples onto existing principal components"},
-    {"batch", 0, false, "load all genotypes into RAM at once [not in this build]"},
+    {"batch", 0, false, "load all genotypes into RAM at once"},
     {"memory", 'm', true, "size of block, in MB"},
     {"blocksize", 'b', true, "size of block for, in number of SNPs"},
     {"numthreads", 'n', true, "set number of OpenMP threads"},
@@ -246,11 +246,8 @@ int main(int argc, char* argv[]) {
         return EXIT_FAILURE;
       }
     }
-    if (vm.count("batch")) {
-      std::cerr << "Error: --batch (all genotypes as doubles in host RAM) is not part of the "
-                   "B200 build; the packed genotypes are always resident in HBM" << std::endl;
-      return EXIT_FAILURE;
-    }
+    // --batch: all genotypes as doubles (flashpca.cpp:229-234, MEM_MODE_OFFLINE)
+    bool batch = vm.count("batch") && mode == MODE_PCA;
 
     int memory = 2048;
     if (vm.count("memory")) {
@@ -422,6 +419,7 @@ int main(int argc, char* argv[]) {
     data.geno_filename = geno_file;
     data.get_size();
     data.prepare();
+    if (batch) data.read_bed(false);  // flashpca.cpp:597-601
 
     RandomPCA rpca;
     rpca.verbose = verbose;
@@ -471,7 +469,8 @@ int main(int argc, char* argv[]) {
     // ---- the main analysis
     if (mode == MODE_PCA) {
       std::cout << timestamp() << "PCA begin" << std::endl;
-      rpca.pca_fast(data, block_size, n_dim, maxiter, tol, seed, do_loadings);
+      if (batch) rpca.pca_fast(data.X, block_size, n_dim, maxiter, tol, seed, do_loadings);
+      else rpca.pca_fast(data, block_size, n_dim, maxiter, tol, seed, do_loadings);
       std::cout << timestamp() << "PCA done" << std::endl;
     } else if (mode == MODE_CHECK_PCA) {
       rpca.check(data, block_size, eigvecfile, eigvalfile);

@@ -16,6 +16,58 @@ static double divisor_value(int divisor, double n, double p) {
   return 1;
 }
 
+// shared tail of both pca_fast overloads (randompca.cpp:138-157, 180-210)
+template <class Op>
+static void finish_pca(RandomPCA& r, Op& op, unsigned int N, unsigned int p, unsigned int ndim,
+                       unsigned int maxiter, double tol, bool do_loadings) {
+  r.U = Matrix(N, ndim);
+  Vector evals(ndim);
+  uint32_t nconv = 0, nops_ = 0, niter = 0;
+  if (fpb_pca(op.handle(), ndim, ndim * 2 + 1, maxiter, tol, evals.data(), r.U.data(), &nconv,
+              &nops_, &niter))
+    throw std::runtime_error(fpb_last_error(op.handle()));
+  r.nops = nops_;
+  r.verbose&& std::cout << timestamp() << "Matrix operations: " << nops_
+                        << ", restarts: " << (niter - 1) << std::endl;
+  if (nconv < ndim)
+    // upstream throws a *pointer* here (randompca.cpp:160-165, 212-217) and main's catch(...)
+    // reports an unknown exception; a value is thrown instead so the message survives.
+    throw std::runtime_error(std::string("Spectra eigen-decomposition was not successful") +
+                             ", status: 1 (converged " + std::to_string(nconv) + " of " +
+                             std::to_string(ndim) + ")");
+  double div = divisor_value(r.divisor, N, p);
+  r.d.resize(ndim);
+  for (unsigned int j = 0; j < ndim; j++) r.d[j] = evals[j] / div;  // eigenvalues, not singular values
+  if (do_loadings) {
+    r.verbose&& std::cout << "Computing loadings" << std::endl;
+    r.V = op.crossprod2(r.U);
+    for (unsigned int j = 0; j < ndim; j++) {
+      double s = r.d[j];
+      for (unsigned int i = 0; i < p; i++) r.V(i, j) = r.V(i, j) * (1.0 / sqrt(s)) / sqrt(div);
+    }
+  }
+  r.trace = op.trace / div;
+  r.pve.resize(ndim);
+  r.Px = Matrix(N, ndim);
+  for (unsigned int j = 0; j < ndim; j++) {
+    r.pve[j] = r.d[j] / r.trace;
+    double sd = sqrt(r.d[j]);
+    for (unsigned int i = 0; i < N; i++) r.Px(i, j) = r.U(i, j) * sd;
+  }
+  r.verbose&& std::cout << timestamp() << "GRM trace: " << r.trace << std::endl;
+}
+
+void RandomPCA::pca_fast(Matrix& X, unsigned int block_size, unsigned int ndim,
+                         unsigned int maxiter, double tol, long seed, bool do_loadings) {
+  (void)block_size;
+  (void)seed;
+  // X_meansd = standardise(X, stand_method_x); SVDWide op(X)   (randompca.cpp:127-130)
+  SVDWide op(X, stand_method_x, verbose, device);
+  X_meansd = op.meansd();
+  finish_pca(*this, op, (unsigned int)X.rows(), (unsigned int)X.cols(), ndim, maxiter, tol,
+             do_loadings);
+}
+
 void RandomPCA::pca_fast(Data& dat, unsigned int block_size, unsigned int ndim,
                          unsigned int maxiter, double tol, long seed, bool do_loadings) {
   (void)seed;  // upstream never uses it for PCA either (randompca.cpp:168-178)
@@ -24,46 +76,8 @@ void RandomPCA::pca_fast(Data& dat, unsigned int block_size, unsigned int ndim,
 
   // Spectra::SymEigsSolver<double, LARGEST_ALGE, SVDWideOnline> eigs(&op, ndim, 2*ndim+1);
   // eigs.init(); eigs.compute(maxiter, tol);   -- run with the basis resident in HBM
-  U = Matrix(N, ndim);
-  Vector evals(ndim);
-  uint32_t nconv = 0, nops_ = 0, niter = 0;
-  if (fpb_pca(op.handle(), ndim, ndim * 2 + 1, maxiter, tol, evals.data(), U.data(), &nconv,
-              &nops_, &niter))
-    throw std::runtime_error(fpb_last_error(op.handle()));
-  nops = nops_;
-  verbose&& std::cout << timestamp() << "Matrix operations: " << nops_ << ", restarts: "
-                      << (niter - 1) << std::endl;
-
-  double div = divisor_value(divisor, N, p);
-
-  if (nconv >= ndim) {
-    d.resize(ndim);
-    for (unsigned int j = 0; j < ndim; j++) d[j] = evals[j] / div;  // eigenvalues, not singular values
-    if (do_loadings) {
-      verbose&& std::cout << "Computing loadings" << std::endl;
-      V = op.crossprod2(U);
-      for (unsigned int j = 0; j < ndim; j++) {
-        double s = d[j];
-        for (unsigned int i = 0; i < p; i++) V(i, j) = V(i, j) * (1.0 / sqrt(s)) / sqrt(div);
-      }
-    }
-    trace = op.trace / div;
-    pve.resize(ndim);
-    Px = Matrix(N, ndim);
-    for (unsigned int j = 0; j < ndim; j++) {
-      pve[j] = d[j] / trace;
-      double sd = sqrt(d[j]);
-      for (unsigned int i = 0; i < N; i++) Px(i, j) = U(i, j) * sd;
-    }
-    X_meansd = dat.X_meansd;
-    verbose&& std::cout << timestamp() << "GRM trace: " << trace << std::endl;
-  } else {
-    // upstream throws a *pointer* here (randompca.cpp:212-217) and main's catch(...)
-    // reports an unknown exception; a value is thrown instead so the message survives.
-    throw std::runtime_error(std::string("Spectra eigen-decomposition was not successful") +
-                             ", status: 1 (converged " + std::to_string(nconv) + " of " +
-                             std::to_string(ndim) + ")");
-  }
+  finish_pca(*this, op, N, p, ndim, maxiter, tol, do_loadings);
+  X_meansd = dat.X_meansd;
 }
 
 void RandomPCA::check(Data& dat, unsigned int block_size, std::string evec_file,

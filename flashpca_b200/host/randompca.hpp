@@ -24,6 +24,9 @@ class RandomPCA {
   int device = 0;
   unsigned int nops = 0;
 
+  // randompca.cpp:121-166 (in-memory matrix of dosages, NaN = missing)
+  void pca_fast(Matrix& X, unsigned int block_size, unsigned int ndim, unsigned int maxiter,
+                double tol, long seed, bool do_loadings);
   // randompca.cpp:168-218
   void pca_fast(Data& dat, unsigned int block_size, unsigned int ndim, unsigned int maxiter,
                 double tol, long seed, bool do_loadings);

@@ -18,6 +18,53 @@
 
 namespace flashpca {
 
+// Drop-in for upstream class SVDWide (svdwide.h:9-30): the operator of the
+// in-memory path.  Upstream standardises the matrix on the host first
+// (randompca.cpp:127 -> util.cpp:24-192) and keeps a reference to it; here the
+// raw dosage matrix (NaN = missing) is copied to HBM and standardised there,
+// and X_meansd / trace are available from the operator.
+class SVDWide {
+ public:
+  SVDWide(const Matrix& raw, int stand_method, bool verbose_ = false, int device = 0)
+      : n((unsigned int)raw.rows()), p((unsigned int)raw.cols()) {
+    verbose = verbose_;
+    nops = 1;
+    if (fpb_create_dense(&h, raw.data(), raw.rows(), raw.cols(), stand_method, device))
+      throw std::runtime_error(fpb_last_error(nullptr));
+    fpb_get_trace(h, &trace);
+  }
+  ~SVDWide() { fpb_destroy(h); }
+  SVDWide(const SVDWide&) = delete;
+  SVDWide& operator=(const SVDWide&) = delete;
+
+  inline unsigned int rows() const { return n; }
+  inline unsigned int cols() const { return n; }
+  // y = mat * (mat' x)   (svdwide.cpp:4-12)
+  void perform_op(const double* x_in, double* y_out) {
+    if (fpb_perform_op(h, x_in, y_out)) throw std::runtime_error(fpb_last_error(h));
+    nops++;
+  }
+  Matrix crossprod2(const Matrix& x) {  // mat' * x, for the loadings (randompca.cpp:151-152)
+    Matrix Y(p, x.cols());
+    if (fpb_crossprod_multi(h, x.data(), (uint32_t)x.cols(), Y.data()))
+      throw std::runtime_error(fpb_last_error(h));
+    return Y;
+  }
+  Matrix meansd() {
+    Matrix m(p, 2);
+    if (fpb_get_meansd(h, m.data())) throw std::runtime_error(fpb_last_error(h));
+    return m;
+  }
+  double trace = 0;  // sum of squares of the standardised matrix (randompca.cpp:154)
+  fpb_handle* handle() { return h; }
+
+ private:
+  const unsigned int n, p;
+  bool verbose;
+  unsigned int nops;
+  fpb_handle* h = nullptr;
+};
+
 class SVDWideOnline {
  public:
   double trace = 0;  // svdwide.h:37 (known right after staging)

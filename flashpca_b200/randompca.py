@@ -52,6 +52,31 @@ class RandomPCA:
                 op.close()
         return self
 
+    def pca_fast_matrix(self, x, ndim: int, maxiter: int, tol: float, seed: int = 1,
+                        do_loadings: bool = False, device: int = 0):
+        """randompca.cpp:121-166 (the MatrixXd overload; flashpca_internal,
+        flashpcaR/src/flashpca.cpp:17-93; `flashpca --batch`)."""
+        from .svdwide import SVDWide
+        op = SVDWide(x, self.stand_method_x, self.verbose, device)
+        try:
+            n, p = op.n, op.p
+            res = op.pca(ndim, 2 * ndim + 1, maxiter, tol)
+            self.nops = res["nops"]
+            if res["nconv"] < ndim:
+                raise FpbError("Spectra eigen-decomposition was not successful, status: 1")
+            div = self._div(n, p)
+            self.U = res["vectors"]
+            self.d = res["values"] / div
+            if do_loadings:  # randompca.cpp:149-153
+                self.V = op.crossprod2(self.U) / np.sqrt(self.d)[None, :] / np.sqrt(div)
+            self.trace = op.trace / div
+            self.pve = self.d / self.trace
+            self.Px = self.U * np.sqrt(self.d)[None, :]
+            self.X_meansd = op.meansd()
+        finally:
+            op.close()
+        return self
+
     def check(self, dat, block_size: int, evec: np.ndarray, evals: np.ndarray, device: int = 0,
               op: SVDWideOnline | None = None):
         """randompca.cpp:663-703: err_j = || X X' u_j / div - u_j d_j ||^2."""

@@ -20,6 +20,40 @@ def _f64(a, rows):
     return np.asfortranarray(a)
 
 
+class SVDWide:
+    """svdwide.h:9-30 + standardise() (util.cpp:24-192): the in-memory operator of
+    RandomPCA::pca_fast(MatrixXd&, ...).  `mat` is an N x P dosage matrix with NaN
+    for missing; it is copied to HBM and standardised there."""
+
+    def __init__(self, mat, stand_method: int = 3, verbose: bool = False, device: int = 0):
+        self.lib = _lib.load()
+        x = np.asfortranarray(np.asarray(mat, dtype=np.float64))
+        if x.ndim != 2:
+            raise FpbError("X must be a matrix")
+        self.n, self.p = x.shape
+        self.h = ctypes.c_void_p()
+        check(self.lib.fpb_create_dense(ctypes.byref(self.h), x.ctypes.data, self.n, self.p,
+                                        int(stand_method), device))
+        self.nops = 1
+
+    close = lambda self: SVDWideOnline.close(self)
+    __del__ = lambda self: SVDWideOnline.__del__(self)
+    rows = lambda self: self.n
+    cols = lambda self: self.n
+    trace = property(lambda self: SVDWideOnline.trace.fget(self))
+    meansd = lambda self: SVDWideOnline.meansd(self)
+    _call = lambda self, *a: SVDWideOnline._call(self, *a)
+    perform_op = lambda self, x, y=None: SVDWideOnline.perform_op(self, x, y)
+    crossprod2 = lambda self, x: SVDWideOnline.crossprod2(self, x)
+    prod3 = lambda self, x: SVDWideOnline.prod3(self, x)
+    pca = lambda self, *a: SVDWideOnline.pca(self, *a)
+
+    def standardised(self) -> np.ndarray:
+        out = np.zeros((self.n, self.p), order="F")
+        check(self.lib.fpb_get_dense(self.h, out.ctypes.data), self.h)
+        return out
+
+
 class SVDWideOnline:
     """svdwide.h:32-107.  `dat` is a flashpca_b200.Data (or None when the packed
     genotypes are given directly)."""

@@ -78,6 +78,18 @@ int fpb_create_synthetic(fpb_handle **out, uint64_t n_individuals, uint64_t nsnp
                          const uint32_t *thresholds, uint32_t npop, uint32_t missing_threshold,
                          uint64_t seed, int stand_method, int device);
 
+/* fpb_create_dense: the in-memory matrix path -- RandomPCA::pca_fast(MatrixXd&, ...)
+ * (randompca.cpp:121-166) with SVDWide (svdwide.h:9-30, svdwide.cpp:4-12).  x is an
+ * N x P column-major matrix of dosages, NaN = missing; it is copied to HBM and
+ * standardised there exactly as standardise() does (util.cpp:24-192):
+ * stand_method 0 none, 1 sd, 2 binom, 3 binom2, 4 center (util.h:34-38).
+ * The handle then serves the same operator family; fpb_get_meansd returns the
+ * (mean, sd) table standardise() returns, fpb_get_trace the sum of squares
+ * (randompca.cpp:154), fpb_get_dense the standardised matrix. */
+int fpb_create_dense(fpb_handle **out, const double *x, uint64_t n_individuals, uint64_t nsnps,
+                     int stand_method, int device);
+int fpb_get_dense(fpb_handle *h, double *out_x);
+
 void fpb_destroy(fpb_handle *h);
 
 /* ---- shape, statistics -------------------------------------------------- */

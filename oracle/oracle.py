@@ -125,6 +125,48 @@ def dense_standardise(codes: np.ndarray, stand_method: int = STANDARDISE_BINOM2,
     return x, meansd
 
 
+def standardise_matrix(x: np.ndarray, method: int):
+    """util.cpp:24-192 standardise(X, method): methods 0 none, 1 sd, 2 binom,
+    3 binom2, 4 center (util.h:34-38); NaN = missing.  Returns (X', meansd)."""
+    x = np.array(x, dtype=np.float64, order="F")
+    n, p = x.shape
+    na = np.isnan(x)
+    cnt = (~na).sum(axis=0).astype(np.float64)
+    if method in (0, 4):
+        mean = np.nansum(x, axis=0) / cnt
+        sd = np.ones(p)
+        if method == 0:
+            out = np.where(na, mean[None, :], x)
+        else:
+            out = np.where(na, 0.0, x - mean[None, :])
+    elif method == 1:
+        k = 1.0
+        s = np.nansum(x - k, axis=0)
+        sq = np.nansum((x - k) ** 2, axis=0)
+        var = (sq - s * s / cnt) / (cnt - 1)
+        mean = (s + k * cnt) / cnt
+        sd = np.sqrt(var)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z = (x - mean[None, :]) / sd[None, :]
+        out = np.where(na, 0.0, np.where(sd[None, :] > VAR_TOL, z, mean[None, :]))
+    elif method in (2, 3):
+        mean = np.nansum(x, axis=0) / cnt
+        r = mean / 2.0
+        sd = np.sqrt((1.0 if method == 2 else 2.0) * r * (1.0 - r))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z = (x - mean[None, :]) / sd[None, :]
+        out = np.where(na, 0.0, np.where(sd[None, :] > VAR_TOL, z, mean[None, :]))
+    else:
+        raise ValueError("unknown standardization method")
+    return np.asfortranarray(out), np.stack([mean, sd], axis=1)
+
+
+def dosage_matrix(codes: np.ndarray) -> np.ndarray:
+    """decode_plink (data.cpp:65-126) as doubles with NaN for missing: what
+    flashpcaR hands to flashpca_internal for a genotype matrix."""
+    return np.array([2.0, np.nan, 1.0, 0.0])[codes]
+
+
 def dense_pca(x: np.ndarray, ndim: int, divisor: int = DIVISOR_P):
     """randompca.cpp:180-210 applied to a dense eigh of X X' (the criterion of
     test_pca.R:47,70).  Returns dict(d, U, Px, pve, trace)."""

@@ -84,6 +84,26 @@ def test_cli_pca_outputs_match_dense(cli, tmp_path):
     assert np.abs(proj - pcs).max() < 1e-5 * np.abs(pcs).max()
 
 
+def test_cli_batch_mode_matches_online(cli, tmp_path):
+    """--batch (read_bed + standardise + SVDWide, flashpca.cpp:597-601,
+    randompca.cpp:121-166) and the default online mode give the same PCA."""
+    stem = FIXTURES["data_chr1"]
+    for tag, extra in (("online", []), ("batch", ["--batch"])):
+        out = subprocess.run([cli, "--bfile", stem, "--ndim", "5", "--tol", "1e-9", "--notime",
+                              "--precision", "17", "--suffix", "_%s.txt" % tag] + extra,
+                             cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+    a = np.loadtxt(tmp_path / "eigenvalues_online.txt")
+    b = np.loadtxt(tmp_path / "eigenvalues_batch.txt")
+    assert np.abs(a / b - 1).max() < 1e-9
+    _, _, ua = _read_table(tmp_path / "eigenvectors_online.txt")
+    _, _, ub = _read_table(tmp_path / "eigenvectors_batch.txt")
+    assert np.abs(O.sign_align(ua, ub) - ub).max() < 1e-7
+    _, payload, n, p = load_fixture("data_chr1")
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    assert np.abs(b / O.dense_pca(x, 5)["d"] - 1).max() < 1e-6
+
+
 def test_cli_default_precision_and_errors(cli, tmp_path):
     stem = FIXTURES["data_chr1"]
     out = subprocess.run([cli, "--bfile", stem, "--ndim", "3", "--notime", "--suffix", ".tsv"],

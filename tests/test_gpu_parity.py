@@ -355,3 +355,35 @@ def test_full_size_properties(native_lib, n, p):
     assert np.array_equal(op.meansd()[:64], orc.meansd())
     # trace: every non-monomorphic SNP contributes about its non-missing count * var ratio
     assert 0.5 * n * p < op.trace < 1.5 * n * p
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4])
+def test_in_memory_matrix_path(native_lib, method):
+    """RandomPCA::pca_fast(MatrixXd&) with SVDWide + standardise(), all five
+    standardisation methods, against eigen(tcrossprod(S)/ncol(S)) of the
+    oracle-standardised matrix: the flashpcaR test (test_pca.R:45-105, tol 1e-4;
+    tighter here) on its own fixture."""
+    from flashpca_b200 import RandomPCA, SVDWide
+    _, payload, n, p = load_fixture("data_chr1")
+    x = O.dosage_matrix(O.dense_codes(payload, n, p))
+    s_ref, msd_ref = O.standardise_matrix(x, method)
+    op = SVDWide(x, method)
+    assert np.allclose(op.meansd(), msd_ref, rtol=1e-12, atol=1e-13)
+    assert np.abs(op.standardised() - s_ref).max() <= 1e-11 * np.abs(s_ref).max()
+    v = np.random.default_rng(method).standard_normal(n)
+    y_ref = s_ref @ (s_ref.T @ v)
+    assert _relerr(op.perform_op(v), y_ref) <= 1e-11          # svdwide.cpp:10
+    assert abs(op.trace / np.sum(s_ref * s_ref) - 1) < 1e-12
+    ref = O.dense_pca(s_ref, 10)
+    r = RandomPCA()
+    r.stand_method_x = method
+    r.pca_fast_matrix(x, 10, 500, 1e-8, do_loadings=True)
+    assert np.abs(r.d / ref["d"] - 1).max() < 1e-6
+    assert np.abs(r.pve / ref["pve"] - 1).max() < 1e-6
+    u = O.sign_align(r.U, ref["U"])
+    assert np.abs(u - ref["U"]).max() < 1e-6
+    vref = O.dense_loadings(s_ref, ref["U"], ref["d"], ref["div"])
+    assert np.abs(O.sign_align(r.V, vref) - vref).max() < 1e-6 * np.abs(vref).max()
+    if method in (2, 3):  # the bed path and the matrix path agree (test_pca.R:108-131)
+        opb = _mk(payload, n, p, stand_method=method)
+        assert _relerr(opb.perform_op(v), y_ref) <= 1e-11

@@ -166,3 +166,28 @@ def test_irlm_restatement_vs_dense(name, ndim, golden):
     u = O.sign_align(res["U"], dres["U"])
     assert np.abs(u - dres["U"]).max() < 5e-6
     assert 1 + 2 * ndim <= res["nops"] <= 400
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4])
+def test_standardise_matrix_restatement(method):
+    """util.cpp:24-192 restatement vs the formulas flashpcaR's tests use
+    (test_standardisation.R:15-86: scale()/scale2() with NA -> 0)."""
+    _, payload, n, p = load_fixture("data_chr1")
+    x = O.dosage_matrix(O.dense_codes(payload, n, p))[:, :200]
+    s, msd = O.standardise_matrix(x, method)
+    mu = np.nanmean(x, axis=0)
+    assert np.allclose(msd[:, 0], mu, rtol=1e-13)
+    if method == 0:
+        assert np.allclose(s, np.where(np.isnan(x), mu, x))
+    elif method == 4:
+        assert np.allclose(s, np.where(np.isnan(x), 0, x - mu))
+    else:
+        if method == 1:
+            sd = np.nanstd(x, axis=0, ddof=1)
+        else:
+            sd = np.sqrt((1 if method == 2 else 2) * (mu / 2) * (1 - mu / 2))
+        assert np.allclose(msd[:, 1], sd, rtol=1e-12)
+        assert np.allclose(s, np.where(np.isnan(x), 0, (x - mu) / sd), rtol=1e-11, atol=1e-12)
+    if method == 3:   # the matrix path and the bed path standardise identically
+        xb, _ = O.dense_standardise(O.dense_codes(payload, n, p)[:, :200])
+        assert np.allclose(s, xb, rtol=1e-13, atol=1e-13)
