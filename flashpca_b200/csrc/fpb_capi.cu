@@ -114,10 +114,11 @@ struct fpb_handle {
   uint32_t gtiles_s = 0, gtiles_i = 0;
   uint4* d_slices = nullptr;
   double* d_part = nullptr;
-  double *d_a = nullptr, *d_b = nullptr, *d_corr = nullptr;
-  double *d_pmax = nullptr, *d_psum = nullptr;
+  double *d_a = nullptr, *d_corr = nullptr;
+  double *d_pmax = nullptr, *d_psum = nullptr;  // (max|v|, sum) block partials of the next vector
+  uint32_t nparts = 0;
   double *d_mx = nullptr, *d_mc = nullptr;  // per-SNP / per-individual missing-genotype sums
-  fpb::VecScale* d_sc = nullptr;  // [0] = x, [1] = a, [2] = b
+  fpb::VecScale* d_sc = nullptr;  // [0] = x, [1] = (step of a, sum of b)
   uint32_t nchunks_s = 0, nchunks_i = 0, splits_s = 1, splits_i = 1, cps_s = 1, cps_i = 1;
   // TMA kernel variant: tensor maps over gs / gi, 128-byte stages
   bool use_tma = false;
@@ -464,11 +465,11 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
                              std::max(std::max(h->splits_s, h->splits_i),
                                       std::max(h->tsplits_s, h->tsplits_i))));
   FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * h->nsnps));
-  FPB_CUDA(h, cudaMalloc(&h->d_b, sizeof(double) * h->nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * h->nsnps));
-  FPB_CUDA(h, cudaMalloc(&h->d_pmax, sizeof(double) * kVecBlocks));
-  FPB_CUDA(h, cudaMalloc(&h->d_psum, sizeof(double) * kVecBlocks));
-  FPB_CUDA(h, cudaMalloc(&h->d_sc, sizeof(fpb::VecScale) * 3));
+  const size_t max_parts = std::max<size_t>(kVecBlocks, (h->nsnps + 255) / 256);
+  FPB_CUDA(h, cudaMalloc(&h->d_pmax, sizeof(double) * max_parts));
+  FPB_CUDA(h, cudaMalloc(&h->d_psum, sizeof(double) * max_parts));
+  FPB_CUDA(h, cudaMalloc(&h->d_sc, sizeof(fpb::VecScale) * 2));
   if (h->nmissing) {
     FPB_CUDA(h, cudaMalloc(&h->d_mx, sizeof(double) * h->nsnps * h->gtiles_s));
     FPB_CUDA(h, cudaMalloc(&h->d_mc, sizeof(double) * h->n * h->gtiles_i));
@@ -534,10 +535,11 @@ void generic_prod(fpb_handle* h, const double* d_v, double* d_y) {
 
 // ------------------------------ tensor path --------------------------------
 
-void vec_prepare(fpb_handle* h, const double* d_v, uint64_t len, int slot) {
+// (max|v|, sum v) block partials of a vector produced outside the library's kernels
+void vec_partials(fpb_handle* h, const double* d_v, uint64_t len) {
   fpb::k_vec_partial<<<kVecBlocks, 256, 0, h->stream>>>(d_v, len, h->d_pmax, h->d_psum);
-  fpb::k_vec_final<<<1, 32, 0, h->stream>>>(h->d_pmax, h->d_psum, kVecBlocks, h->d_sc + slot);
-  h->launches += 2;
+  h->nparts = kVecBlocks;
+  h->launches++;
 }
 
 // part[split][row] = sum_s 128^s sum_col G[row][col] * digit_s(v[col]);
@@ -549,8 +551,8 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
   const uint32_t rows = (uint32_t)(snp_major ? h->nsnps : h->n);
   const uint32_t nchunks = snp_major ? h->nchunks_s : h->nchunks_i;
   uint32_t nwq = nchunks * fpb::kChunkWords;  // covers the TMA stages as well
-  fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(d_v, vlen, nwq, h->d_sc + slot,
-                                                             h->d_slices);
+  fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(
+      d_v, vlen, nwq, h->d_pmax, h->d_psum, h->nparts, h->d_sc + slot, h->d_slices);
   h->launches += 2;
   if (h->time_gemv) cudaEventRecord(h->kev[snp_major ? 0 : 2], h->stream);
   struct StopTimer {  // records the closing event when the launch has been enqueued
@@ -584,8 +586,9 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
 
 // Sparse missing-genotype sums on the side stream.  fork_mark() pins the point
 // of the main stream the gather depends on (its input vector is complete);
-// gather_launch() enqueues it; join_gather() makes the main stream wait for the
-// result before the finalize kernel.
+// gather_launch() enqueues it (it runs ahead of / next to the slicing kernels);
+// join_gather() makes the main stream wait for the result before the finalize
+// kernel.
 void fork_mark(fpb_handle* h) { cudaEventRecord(h->ev_fork, h->stream); }
 void gather_launch(fpb_handle* h, bool by_snp, const double* vec) {
   const uint64_t nrows = by_snp ? h->nsnps : h->n, veclen = by_snp ? h->n : h->nsnps;
@@ -605,44 +608,40 @@ void gather_launch(fpb_handle* h, bool by_snp, const double* vec) {
 }
 void join_gather(fpb_handle* h) { cudaStreamWaitEvent(h->stream, h->ev_join, 0); }
 
-// first half: t = X'x (d_t) and/or the a, b, corr inputs of the second half
+// first half: t = X'x (d_t) and/or the a, corr inputs of the second half
 void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_half) {
-  const bool gfirst = true;
-  if (h->nmissing) fork_mark(h);
-  if (h->nmissing && gfirst) gather_launch(h, true, d_x);
-  vec_prepare(h, d_x, h->n, 0);
-  const uint32_t nsplits = imma_contract(h, true, d_x, h->n, 0);
   if (h->nmissing) {
-    if (!gfirst) gather_launch(h, true, d_x);
-    join_gather(h);
+    fork_mark(h);
+    gather_launch(h, true, d_x);
   }
+  vec_partials(h, d_x, h->n);
+  const uint32_t nsplits = imma_contract(h, true, d_x, h->n, 0);
+  if (h->nmissing) join_gather(h);
   uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
   fpb::k_finalize_crossprod<<<gb, 256, 0, h->stream>>>(
       h->d_part, nsplits, h->part_stride, (uint32_t)h->nsnps, h->d_sc + 0, h->d_scale,
-      h->nmissing ? h->d_mx : nullptr, h->gtiles_s, d_t, second_half ? h->d_a : nullptr, h->d_b, h->d_corr);
+      h->nmissing ? h->d_mx : nullptr, h->gtiles_s, d_t, second_half ? h->d_a : nullptr,
+      h->d_corr, h->d_pmax, h->d_psum);
+  if (second_half) h->nparts = gb;
   h->launches++;
 }
 
-// second half from a, b, corr already in the handle: y = F - Sb + missing terms
+// second half from a, corr and the (max|a|, sum b) partials already in the handle
 void imma_prod_tail(fpb_handle* h, double* d_y) {
-  const bool gfirst = true;
-  if (h->nmissing) fork_mark(h);
-  if (h->nmissing && gfirst) gather_launch(h, false, h->d_corr);
-  vec_prepare(h, h->d_a, h->nsnps, 1);
-  vec_prepare(h, h->d_b, h->nsnps, 2);
-  const uint32_t nsplits = imma_contract(h, false, h->d_a, h->nsnps, 1);
   if (h->nmissing) {
-    if (!gfirst) gather_launch(h, false, h->d_corr);
-    join_gather(h);
+    fork_mark(h);
+    gather_launch(h, false, h->d_corr);
   }
+  const uint32_t nsplits = imma_contract(h, false, h->d_a, h->nsnps, 1);
+  if (h->nmissing) join_gather(h);
   uint32_t gb = (uint32_t)((h->n + 255) / 256);
   fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, nsplits, h->part_stride, h->n,
-                                                  h->d_sc + 1, h->d_sc + 2,
-                                                  h->nmissing ? h->d_mc : nullptr, h->gtiles_i,
-                                                  d_y);
+                                                  h->d_sc + 1, h->nmissing ? h->d_mc : nullptr,
+                                                  h->gtiles_i, d_y);
   h->launches++;
 }
 
+// in-memory matrix path (svdwide.cpp:4-12)
 void dense_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
   fpb::k_dense_gemv_t<<<(uint32_t)h->nsnps, 256, 0, h->stream>>>(h->d_X, h->n, d_x, d_t);
   h->launches++;
@@ -670,7 +669,8 @@ void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
   } else if (h->use_imma) {
     uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
     fpb::k_prod_inputs<<<gb, 256, 0, h->stream>>>(d_v, h->d_scale, (uint32_t)h->nsnps, h->d_a,
-                                                  h->d_b, h->d_corr);
+                                                  h->d_corr, h->d_pmax, h->d_psum);
+    h->nparts = gb;
     h->launches++;
     imma_prod_tail(h, d_y);
   } else {
@@ -922,7 +922,6 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_slices);
   cudaFree(h->d_part);
   cudaFree(h->d_a);
-  cudaFree(h->d_b);
   cudaFree(h->d_corr);
   cudaFree(h->d_pmax);
   cudaFree(h->d_psum);

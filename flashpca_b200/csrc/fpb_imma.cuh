@@ -42,10 +42,9 @@ constexpr int kChunkBytes = 512; // packed bytes of one row per pipeline chunk (
 constexpr int kChunkWords = kChunkBytes / 4;     // 128 word-columns
 constexpr int kFlushChunks = 32;                 // int32 accumulators -> FP64 every 65536 columns
 
-struct VecScale {   // written by k_vec_prepare, read by slicing / finalize kernels
-  double sum;       // sum of the vector (deterministic order)
+struct VecScale {   // written by k_slice_vec, read by the finalize kernels
+  double sum;       // sum of a vector (deterministic order)
   double delta;     // fixed-point step 2^(ex - 54), 0 for an all-zero vector, NaN if non-finite
-  double inv_delta_unused;
   int ex;
   int pad;
 };
@@ -88,13 +87,18 @@ k_vec_partial(const double* __restrict__ v, uint64_t n, double* __restrict__ pma
   }
 }
 
-__global__ void k_vec_final(const double* __restrict__ pmax, const double* __restrict__ psum,
-                            uint32_t nblocks, VecScale* __restrict__ out) {
-  // one warp; lane l combines blocks l, l+32, ... in order, then a fixed shuffle tree
-  const int lane = threadIdx.x;
+// Combine per-block (max|v|, sum) partials into a VecScale.  Called by every
+// thread of a 128-thread block; every block that calls it on the same partials
+// gets the same bits (fixed thread->partial assignment, fixed reduction tree).
+__device__ __forceinline__ VecScale scale_from_partials(const double* __restrict__ pmax,
+                                                        const double* __restrict__ psum,
+                                                        uint32_t nparts) {
+  __shared__ double smx[4], ssm[4];
+  __shared__ VecScale sres;
   double m = 0.0, s = 0.0;
-  for (uint32_t g = lane; g < nblocks; g += 32) {
-    m = (pmax[g] > m || pmax[g] != pmax[g]) ? pmax[g] : m;
+  for (uint32_t g = threadIdx.x; g < nparts; g += 128) {
+    const double pm = pmax[g];
+    m = (pm > m || pm != pm) ? pm : m;
     s += psum[g];
   }
 #pragma unroll
@@ -103,24 +107,63 @@ __global__ void k_vec_final(const double* __restrict__ pmax, const double* __res
     m = (om > m || om != om) ? om : m;
     s += __shfl_xor_sync(0xffffffffu, s, o);
   }
-  if (lane != 0) return;
-  VecScale r;
-  r.sum = s;
-  r.inv_delta_unused = 0.0;
-  r.pad = 0;
-  if (m == 0.0) {
-    r.ex = 0;
-    r.delta = 0.0;
-  } else if (!(m < 1.79e308)) {  // NaN or Inf
-    r.ex = 0;
-    r.delta = nan("");
-  } else {
-    int ex;
-    frexp(m, &ex);  // m = f * 2^ex, 0.5 <= f < 1  ->  |v| < 2^ex
-    r.ex = ex;
-    r.delta = ldexp(1.0, ex - kSliceBits);
+  if ((threadIdx.x & 31) == 0) {
+    smx[threadIdx.x >> 5] = m;
+    ssm[threadIdx.x >> 5] = s;
   }
-  *out = r;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; w++) {
+      m = (smx[w] > m || smx[w] != smx[w]) ? smx[w] : m;
+      s += ssm[w];
+    }
+    VecScale r;
+    r.sum = s;
+    r.pad = 0;
+    if (m == 0.0) {
+      r.ex = 0;
+      r.delta = 0.0;
+    } else if (!(m < 1.79e308)) {  // NaN or Inf
+      r.ex = 0;
+      r.delta = nan("");
+    } else {
+      int ex;
+      frexp(m, &ex);  // m = f * 2^ex, 0.5 <= f < 1  ->  |v| < 2^ex
+      r.ex = ex;
+      r.delta = ldexp(1.0, ex - kSliceBits);
+    }
+    sres = r;
+  }
+  __syncthreads();
+  return sres;
+}
+
+// block-level (max|.|, sum) of one value per thread -> pmax[blockIdx.x], psum[blockIdx.x]
+// (256-thread blocks; used by the kernels that produce the next vector to be sliced)
+__device__ __forceinline__ void emit_block_partials(double absval, double addend,
+                                                    double* __restrict__ pmax,
+                                                    double* __restrict__ psum) {
+  __shared__ double emx[8], esm[8];
+  double m = absval, s = addend;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double om = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (om > m || om != om) ? om : m;
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    emx[threadIdx.x >> 5] = m;
+    esm[threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) {
+      m = (emx[w] > m || emx[w] != emx[w]) ? emx[w] : m;
+      s += esm[w];
+    }
+    pmax[blockIdx.x] = m;
+    psum[blockIdx.x] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -130,15 +173,20 @@ __global__ void k_vec_final(const double* __restrict__ pmax, const double* __res
 // 8 slices of a word-column are rotated by 2*((wq>>2)&3) so that the B-fragment
 // LDS.128 of the contraction kernels (lanes g = slice, q = word-column group)
 // are bank-conflict free when the block is copied verbatim to shared memory.
-// Elements >= n are zero.  nwq = number of word-columns to write.
+// Elements >= n are zero.  nwq = number of word-columns to write.  The scale
+// comes from the (max|v|, sum) block partials written by the kernel that
+// produced v (k_vec_partial, k_finalize_crossprod or k_prod_inputs).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_slice_vec(const double* __restrict__ v, uint64_t n, uint32_t nwq,
-            const VecScale* __restrict__ sc, uint4* __restrict__ out) {
+            const double* __restrict__ pmax, const double* __restrict__ psum, uint32_t nparts,
+            VecScale* __restrict__ sc_out, uint4* __restrict__ out) {
+  const VecScale sc = scale_from_partials(pmax, psum, nparts);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *sc_out = sc;  // for the finalize kernel
   uint32_t wq = blockIdx.x * blockDim.x + threadIdx.x;
   if (wq >= nwq) return;
-  const int ex = sc->ex;
-  const bool live = sc->delta > 0.0;  // false for zero / non-finite vectors
+  const int ex = sc.ex;
+  const bool live = sc.delta > 0.0;  // false for zero / non-finite vectors
   uint32_t dig[8][4] = {};
 #pragma unroll
   for (int b = 0; b < 4; b++) {
@@ -661,17 +709,20 @@ k_sell_gather(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ 
 
 // Finalise X'x for SNP j:
 //   E_j = delta * sum_splits part[s][j];   t_j = [(E_j - 3 Mx_j) - mu_j (Sx - Mx_j)] * inv_sd_j
-// t_out (optional) receives t_j; a_out (optional) receives a_j = t_j * inv_sd_j,
-// b_j = mu_j a_j, corr_j = b_j - 3 a_j (inputs of the second half of perform_op).
+// t_out (optional) receives t_j; a_out (optional) receives a_j = t_j * inv_sd_j and
+// corr_j = b_j - 3 a_j with b_j = mu_j a_j (inputs of the second half of perform_op),
+// plus per-block partials of max|a| and sum b.
 // mxv: mx_tiles x nsnps per-tile partial sums of Mx (null when nothing is missing).
 __global__ void __launch_bounds__(256)
 k_finalize_crossprod(const double* __restrict__ part, uint32_t nsplits, uint64_t stride,
                      uint32_t nsnps, const VecScale* __restrict__ sc,
                      const double2* __restrict__ scale, const double* __restrict__ mxv,
                      uint32_t mx_tiles, double* __restrict__ t_out, double* __restrict__ a_out,
-                     double* __restrict__ b_out, double* __restrict__ corr_out) {
+                     double* __restrict__ corr_out, double* __restrict__ pmax_a,
+                     double* __restrict__ psum_b) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nsnps) return;
+  double abs_a = 0.0, bj = 0.0;
+  if (j < nsnps) {
   double mx = 0.0;
   if (mxv)
     for (uint32_t tt = 0; tt < mx_tiles; tt++) mx += mxv[(uint64_t)tt * nsnps + j];
@@ -686,31 +737,40 @@ k_finalize_crossprod(const double* __restrict__ part, uint32_t nsplits, uint64_t
   if (a_out) {
     double a = dead ? 0.0 : t * ms.y, b = dead ? 0.0 : ms.x * a;
     a_out[j] = a;
-    b_out[j] = b;
     corr_out[j] = b - 3.0 * a;
+    abs_a = fabs(a);
+    bj = b;
   }
+  }
+  // (max|a|, sum b) block partials: the scale of the second half's input vector
+  if (a_out) emit_block_partials(abs_a, bj, pmax_a, psum_b);
 }
 
 // Inputs of prod from a user vector v:  a_j = v_j inv_sd_j, b_j = mu_j a_j, corr_j = b_j - 3 a_j
-__global__ void k_prod_inputs(const double* __restrict__ v, const double2* __restrict__ scale,
-                              uint32_t nsnps, double* __restrict__ a_out,
-                              double* __restrict__ b_out, double* __restrict__ corr_out) {
+__global__ void __launch_bounds__(256)
+k_prod_inputs(const double* __restrict__ v, const double2* __restrict__ scale, uint32_t nsnps,
+              double* __restrict__ a_out, double* __restrict__ corr_out,
+              double* __restrict__ pmax_a, double* __restrict__ psum_b) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nsnps) return;
-  double2 ms = scale[j];
-  double a = v[j] * ms.y, b = ms.x * a;
-  if (ms.y == 0.0) { a = 0.0; b = 0.0; }
-  a_out[j] = a;
-  b_out[j] = b;
-  corr_out[j] = b - 3.0 * a;
+  double a = 0.0, b = 0.0;
+  if (j < nsnps) {
+    double2 ms = scale[j];
+    a = v[j] * ms.y;
+    b = ms.x * a;
+    if (ms.y == 0.0) { a = 0.0; b = 0.0; }
+    a_out[j] = a;
+    corr_out[j] = b - 3.0 * a;
+  }
+  emit_block_partials(fabs(a), b, pmax_a, psum_b);
 }
 
 // Finalise X v for individual i:
 //   y_i = delta_a * sum_splits part[s][i] - Sb + mc_i,  mc_i = sum_{j missing} corr_j
+// (sc_ab holds the step of a and the sum of b)
 __global__ void __launch_bounds__(256)
 k_finalize_prod(const double* __restrict__ part, uint32_t nsplits, uint64_t stride, uint64_t n,
-                const VecScale* __restrict__ sc_a, const VecScale* __restrict__ sc_b,
-                const double* __restrict__ mcv, uint32_t mc_tiles, double* __restrict__ y) {
+                const VecScale* __restrict__ sc_ab, const double* __restrict__ mcv,
+                uint32_t mc_tiles, double* __restrict__ y) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double f = 0.0;
@@ -718,7 +778,7 @@ k_finalize_prod(const double* __restrict__ part, uint32_t nsplits, uint64_t stri
   double mc = 0.0;
   if (mcv)
     for (uint32_t tt = 0; tt < mc_tiles; tt++) mc += mcv[(uint64_t)tt * n + i];
-  y[i] = f * sc_a->delta - sc_b->sum + mc;
+  y[i] = f * sc_ab->delta - sc_ab->sum + mc;  // delta of a, sum of b
 }
 
 }  // namespace fpb
