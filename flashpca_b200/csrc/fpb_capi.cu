@@ -2,7 +2,7 @@
 //
 // Host-side state of one staged genotype matrix (or SNP shard of one):
 //   d_gs     nsnps x pitch_s bytes  SNP-major 2-bit dosage codes (fpb_kernels.cuh)
-//   d_gi     N x pitch_i bytes      individual-major copy (tensor path only)
+//   d_gi     N x pitch_i bytes      individual-major copy (two-copy kernel variants only)
 //   d_scale  nsnps x (mean, 1/sd)   d_lut  nsnps x double4 (generic path table)
 //   d_meansd nsnps x 2              Data::X_meansd (data.cpp:290-291)
 //   CSR lists of the missing genotypes by SNP and by individual (tensor path)
@@ -26,6 +26,8 @@
 #include <vector>
 
 #include <stdlib.h>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "fpb_dense.cuh"
 #include "fpb_imma.cuh"
@@ -124,6 +126,9 @@ struct fpb_handle {
   bool use_tma = false;
   fpb::TmaDesc tm_s, tm_i;
   uint32_t nstages_s = 0, nstages_i = 0, tsplits_s = 1, tsplits_i = 1, sps_s = 1, sps_i = 1;
+  // single-copy mode: the second half also reads gs (k_imma_gemv_tma_t); gi is not kept
+  bool single_copy = false;
+  uint32_t ttiles = 0, ttsplits = 1, ttps = 1;
   uint64_t part_stride = 0;
   // host-pointer API staging (grown on demand)
   double* d_in = nullptr;
@@ -267,21 +272,20 @@ void pick_splits(uint32_t rows, uint32_t nchunks, int sm_count, uint32_t* splits
   *splits = (nchunks + *cps - 1) / *cps;
 }
 
-// Column-blocked, row-sliced (SELL-32 per tile) lists of the missing entries of a
-// packed matrix G (rows x pitch); see fpb_imma.cuh.  Returns 2 when the padded
-// layout would be wasteful (very uneven rows): the caller then uses the generic path.
-int build_blocked_lists(fpb_handle* h, const uint8_t* G, uint64_t rows, uint64_t pitch,
-                        uint64_t veclen, const uint64_t* d_rowptr, uint64_t** d_blkoff,
-                        uint16_t** d_col16, uint32_t* ntiles_out) {
+// Column-blocked, row-sliced (SELL-32 per tile) lists (fpb_imma.cuh) from a CSR
+// (d_rowptr: rows + 1, d_col: ascending columns per row).  Returns 2 when the
+// padded layout would be wasteful (very uneven rows): the caller then uses the
+// generic path.
+int build_blocked_lists(fpb_handle* h, uint64_t rows, uint64_t veclen, const uint64_t* d_rowptr,
+                        const uint32_t* d_col, uint64_t** d_blkoff, uint16_t** d_col16,
+                        uint32_t* ntiles_out) {
   const uint32_t ntiles = (uint32_t)((veclen + fpb::kGatherTile - 1) / fpb::kGatherTile);
   const uint32_t nblk = (uint32_t)((rows + 31) / 32);
   const uint32_t gw = (uint32_t)((rows * 32 + 255) / 256);
-  uint32_t *d_col = nullptr, *d_counts = nullptr, *d_sizes = nullptr;
-  FPB_CUDA(h, cudaMalloc(&d_col, sizeof(uint32_t) * h->nmissing));
+  uint32_t *d_counts = nullptr, *d_sizes = nullptr;
   FPB_CUDA(h, cudaMalloc(&d_counts, sizeof(uint32_t) * (size_t)ntiles * rows));
   FPB_CUDA(h, cudaMalloc(&d_sizes, sizeof(uint32_t) * (size_t)ntiles * nblk));
   FPB_CUDA(h, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)ntiles * rows, h->stream));
-  fpb::k_fill_missing_csr<<<gw, 256, 0, h->stream>>>(G, rows, pitch, d_rowptr, d_col);
   fpb::k_bcsr_count<<<gw, 256, 0, h->stream>>>(d_rowptr, d_col, rows, d_counts);
   uint64_t nwarps = (uint64_t)ntiles * nblk;
   fpb::k_sell_sizes<<<(uint32_t)((nwarps * 32 + 255) / 256), 256, 0, h->stream>>>(
@@ -296,15 +300,50 @@ int build_blocked_lists(fpb_handle* h, const uint8_t* G, uint64_t rows, uint64_t
     FPB_CUDA(h, cudaMemsetAsync(*d_col16, 0x30, sizeof(uint16_t) * padded, h->stream));
     fpb::k_sell_fill<<<gw, 256, 0, h->stream>>>(d_rowptr, d_col, rows, nblk, *d_blkoff, d_counts,
                                                 *d_col16);
-    h->launches += 4;
+    h->launches += 3;
     FPB_CUDA(h, cudaStreamSynchronize(h->stream));
     FPB_CUDA(h, cudaGetLastError());
   }
-  cudaFree(d_col);
   cudaFree(d_counts);
   cudaFree(d_sizes);
   *ntiles_out = ntiles;
   return rc;
+}
+
+// Transpose a CSR (rows_in x rows_out pattern) with a stable radix sort of
+// (column << 32 | row) keys: the result lists ascend, so every later sum has a
+// fixed order.  Staging only; CUB is library code outside the hot path.
+int transpose_csr(fpb_handle* h, uint64_t rows_in, uint64_t rows_out, const uint64_t* d_rowptr,
+                  const uint32_t* d_col, uint64_t** d_rowptr_t, uint32_t** d_col_t) {
+  const uint64_t nnz = h->nmissing;
+  uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
+  uint32_t* d_cnt = nullptr;
+  void* d_tmp = nullptr;
+  FPB_CUDA(h, cudaMalloc(&d_keys, sizeof(uint64_t) * nnz));
+  FPB_CUDA(h, cudaMalloc(&d_keys2, sizeof(uint64_t) * nnz));
+  FPB_CUDA(h, cudaMalloc(&d_cnt, sizeof(uint32_t) * rows_out));
+  FPB_CUDA(h, cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * rows_out, h->stream));
+  fpb::k_csr_to_keys<<<(uint32_t)((rows_in * 32 + 255) / 256), 256, 0, h->stream>>>(
+      d_rowptr, d_col, rows_in, d_keys);
+  size_t tmp_bytes = 0;
+  FPB_CUDA(h, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys2, nnz, 0, 64,
+                                             h->stream));
+  FPB_CUDA(h, cudaMalloc(&d_tmp, tmp_bytes));
+  FPB_CUDA(h, cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys2, nnz, 0, 64,
+                                             h->stream));
+  FPB_CUDA(h, cudaMalloc(d_col_t, sizeof(uint32_t) * nnz));
+  fpb::k_keys_to_csr<<<(uint32_t)((nnz + 255) / 256), 256, 0, h->stream>>>(d_keys2, nnz, *d_col_t,
+                                                                          d_cnt);
+  h->launches += 2;
+  uint64_t total = 0;
+  int rc = build_rowptr(h, d_cnt, rows_out, d_rowptr_t, &total);
+  cudaFree(d_keys);
+  cudaFree(d_keys2);
+  cudaFree(d_cnt);
+  cudaFree(d_tmp);
+  if (rc) return 1;
+  if (total != nnz) FPB_FAIL(h, "internal error: transposed list size mismatch");
+  return 0;
 }
 
 void pick_splits_tma(uint32_t rows, uint32_t nstages, int sm_count, uint32_t* splits,
@@ -393,35 +432,41 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
     return 0;
   }
 
-  // ---- tensor path staging: transposed copy, CSR lists, scratch
-  FPB_CUDA(h, cudaMalloc(&h->d_gi, h->pitch_i * h->n));
-  FPB_CUDA(h, cudaMemsetAsync(h->d_gi, 0, h->pitch_i * h->n, h->stream));
+  // ---- tensor path staging: kernel variant, missing-genotype lists, scratch
   {
+    const char* gv = getenv("FPB_GEMV");
+    h->use_tma = !(gv && !strcmp(gv, "ldg"));
+    h->single_copy = h->use_tma && !(gv && !strcmp(gv, "tma2"));  // tma2 = two-copy TMA variant
+  }
+  if (!h->single_copy) {
+    // two-copy variants keep an individual-major copy for the second half
+    FPB_CUDA(h, cudaMalloc(&h->d_gi, h->pitch_i * h->n));
+    FPB_CUDA(h, cudaMemsetAsync(h->d_gi, 0, h->pitch_i * h->n, h->stream));
     dim3 grid((uint32_t)((h->n + 127) / 128), (uint32_t)((h->nsnps + 127) / 128));
     fpb::k_transpose_2bit<<<grid, 256, 0, h->stream>>>(h->d_gs, h->nsnps, h->pitch_s, h->d_gi,
                                                        h->n, h->pitch_i);
     h->launches++;
   }
   if (h->nmissing) {
-    // by SNP: rows = SNPs, gathered vector = x over individuals
-    int rc = build_blocked_lists(h, h->d_gs, h->nsnps, h->pitch_s, h->n, h->d_rowptr_s,
-                                 &h->d_seg_s, &h->d_col16_s, &h->gtiles_s);
-    if (rc == 1) return 1;
+    // CSR by SNP (columns = individuals, ascending), then its transpose by individual
+    uint32_t *d_col_s = nullptr, *d_col_i = nullptr;
     uint64_t* d_rowptr_i = nullptr;
+    FPB_CUDA(h, cudaMalloc(&d_col_s, sizeof(uint32_t) * h->nmissing));
+    fpb::k_fill_missing_csr<<<gs, 256, 0, h->stream>>>(h->d_gs, h->nsnps, h->pitch_s,
+                                                       h->d_rowptr_s, d_col_s);
+    h->launches++;
+    int rc = build_blocked_lists(h, h->nsnps, h->n, h->d_rowptr_s, d_col_s, &h->d_seg_s,
+                                 &h->d_col16_s, &h->gtiles_s);
     if (rc == 0) {
-      // by individual: rows = individuals, gathered vector = corr over SNPs
-      uint32_t gi = (uint32_t)((h->n * 32 + 255) / 256);
-      fpb::k_row_missing<<<gi, 256, 0, h->stream>>>(h->d_gi, h->n, h->pitch_i, d_cnt);
-      h->launches++;
-      uint64_t total_i = 0;
-      if (build_rowptr(h, d_cnt, h->n, &d_rowptr_i, &total_i)) return 1;
-      if (total_i != h->nmissing)
-        FPB_FAIL(h, "internal error: transposed copy disagrees on missing count");
-      rc = build_blocked_lists(h, h->d_gi, h->n, h->pitch_i, h->nsnps, d_rowptr_i, &h->d_seg_i,
-                               &h->d_col16_i, &h->gtiles_i);
-      cudaFree(d_rowptr_i);
-      if (rc == 1) return 1;
+      rc = transpose_csr(h, h->nsnps, h->n, h->d_rowptr_s, d_col_s, &d_rowptr_i, &d_col_i);
+      if (rc == 0)
+        rc = build_blocked_lists(h, h->n, h->nsnps, d_rowptr_i, d_col_i, &h->d_seg_i,
+                                 &h->d_col16_i, &h->gtiles_i);
     }
+    cudaFree(d_col_s);
+    cudaFree(d_col_i);
+    cudaFree(d_rowptr_i);
+    if (rc == 1) return 1;
     if (rc == 2) {
       // very uneven missingness: padded lists would dominate -> generic FP64 path
       cudaFree(h->d_gi);
@@ -444,26 +489,40 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
   pick_splits((uint32_t)h->n, h->nchunks_i, h->sm_count, &h->splits_i, &h->cps_i);
   h->part_stride = std::max(h->n, h->nsnps);
   {
-    const char* gv = getenv("FPB_GEMV");
-    h->use_tma = !(gv && !strcmp(gv, "ldg"));
     h->nstages_s = (uint32_t)((h->pitch_s + fpb::kTmaStageCols - 1) / fpb::kTmaStageCols);
     h->nstages_i = (uint32_t)((h->pitch_i + fpb::kTmaStageCols - 1) / fpb::kTmaStageCols);
     pick_splits_tma((uint32_t)h->nsnps, h->nstages_s, h->sm_count, &h->tsplits_s, &h->sps_s);
     pick_splits_tma((uint32_t)h->n, h->nstages_i, h->sm_count, &h->tsplits_i, &h->sps_i);
+    if (h->single_copy) {
+      // second half over gs: CTAs = 128-byte column stripes x splits of the 256-row tiles
+      h->ttiles = (uint32_t)((h->nsnps + fpb::kTmaRows - 1) / fpb::kTmaRows);
+      uint32_t stripes = h->nstages_s;
+      uint32_t want = (20u * h->sm_count + stripes - 1) / stripes;
+      uint32_t sp = std::max<uint32_t>(1, std::min<uint32_t>(want, std::max<uint32_t>(1, h->ttiles / 16)));
+      h->ttps = (h->ttiles + sp - 1) / sp;
+      h->ttsplits = (h->ttiles + h->ttps - 1) / h->ttps;
+    }
     if (h->use_tma) {
       if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_s)) return 1;
-      if (make_tensor_map(h, h->d_gi, h->pitch_i, h->n, &h->tm_i)) return 1;
+      if (!h->single_copy && make_tensor_map(h, h->d_gi, h->pitch_i, h->n, &h->tm_i)) return 1;
+      FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma_t,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fpb::kTmaSmemBytes));
       FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        fpb::kTmaSmemBytes));
     }
   }
   uint64_t max_chunks = std::max(h->nchunks_s, h->nchunks_i);
-  FPB_CUDA(h, cudaMalloc(&h->d_slices, sizeof(uint4) * max_chunks * fpb::kChunkWords * 8));
+  // the K-major slices of the single-copy second half need 8 bytes per SNP, padded to whole tiles
+  uint64_t slice_bytes = std::max<uint64_t>(sizeof(uint4) * max_chunks * fpb::kChunkWords * 8,
+                                            (uint64_t)(h->ttiles + 1) * fpb::kTmaTSliceBytes);
+  FPB_CUDA(h, cudaMalloc(&h->d_slices, slice_bytes));
   FPB_CUDA(h, cudaMalloc(&h->d_part,
                          sizeof(double) * h->part_stride *
-                             std::max(std::max(h->splits_s, h->splits_i),
-                                      std::max(h->tsplits_s, h->tsplits_i))));
+                             std::max(std::max(std::max(h->splits_s, h->splits_i),
+                                               std::max(h->tsplits_s, h->tsplits_i)),
+                                      h->ttsplits)));
   FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * h->nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * h->nsnps));
   const size_t max_parts = std::max<size_t>(kVecBlocks, (h->nsnps + 255) / 256);
@@ -546,6 +605,22 @@ void vec_partials(fpb_handle* h, const double* d_v, uint64_t len) {
 // snp_major selects gs (rows = SNPs) or gi (rows = individuals).  Returns the
 // number of splits written.
 uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_t vlen, int slot) {
+  if (!snp_major && h->single_copy) {
+    // F = E a from the SNP-major copy: K-major slices of a, byte-transposing loads
+    const uint32_t ngroups4 = h->ttiles * (fpb::kTmaRows / 4);
+    fpb::k_slice_vec_k<<<(ngroups4 + 127) / 128, 128, 0, h->stream>>>(
+        d_v, vlen, ngroups4, h->d_pmax, h->d_psum, h->nparts, h->d_sc + slot,
+        reinterpret_cast<uint32_t*>(h->d_slices));
+    if (h->time_gemv) cudaEventRecord(h->kev[2], h->stream);
+    dim3 grid(h->nstages_s, h->ttsplits);
+    fpb::k_imma_gemv_tma_t<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
+                             h->stream>>>(h->tm_s, (uint32_t)h->n,
+                                          reinterpret_cast<const uint32_t*>(h->d_slices),
+                                          h->ttiles, h->ttps, h->d_part, h->part_stride);
+    if (h->time_gemv) cudaEventRecord(h->kev[3], h->stream);
+    h->launches += 2;
+    return h->ttsplits;
+  }
   const uint8_t* G = snp_major ? h->d_gs : h->d_gi;
   const uint64_t pitch = snp_major ? h->pitch_s : h->pitch_i;
   const uint32_t rows = (uint32_t)(snp_major ? h->nsnps : h->n);

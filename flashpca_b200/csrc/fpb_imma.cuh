@@ -576,6 +576,162 @@ k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* _
 }
 
 // ---------------------------------------------------------------------------
+// Second half from the SAME SNP-major copy:  F_i = sum_j e_ij a_j.
+//
+// The reduction now runs over SNPs (tile rows), while a packed byte still holds
+// four individuals.  ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 (SASS
+// LDSM.8.MT1616, sm_100a) transposes BYTES on the way to registers and returns
+// exactly the m16n8k32 A fragment: reg0..3 = a0..a3 with M = 16 byte-columns
+// (= 64 individuals) and K = 32 consecutive SNPs (tools/ldsm_probe.cu).  The
+// field masks 0x03/0x0C/0x30/0xC0 then select individual 4*bytecol + f for a
+// whole MMA, so the 4^f factor is uniform per accumulator and is removed in
+// the epilogue; the B operand is the plain digit slices of a_j (K-major).
+//
+// A CTA owns one 128-byte column stripe (512 individuals) and walks a split of
+// the 256-row SNP tiles with the same TMA box / mbarrier ring as above; consumer
+// warp w owns the 16-byte chunk w of the stripe (64 individuals), 4 accumulator
+// sets (one per field).  Per stage and warp: 8 LDSM.x2, 8 LDS.64, 128 LOP3,
+// 32 IMMA.  out[split * out_stride + individual].
+//
+// Slices for this kernel (k_slice_vec_k): per 32 SNPs 256 bytes laid out
+// [slice g][q][b0 (4 digits of SNPs 4q..4q+3) | b1 (SNPs 16+4q..)], i.e. the B
+// fragment of lane (g, q) is one 8-byte load.
+// ---------------------------------------------------------------------------
+constexpr int kTmaTSliceBytes = (kTmaRows / 32) * 256;          // 2 KB per stage
+constexpr int kTmaTStageBytes = kTmaTileBytes + kTmaTSliceBytes;  // 34 KB
+static_assert(kTmaStages * kTmaTStageBytes + 1024 + 128 <= kTmaSmemBytes, "ring too large");
+
+__global__ void __launch_bounds__(128)
+k_slice_vec_k(const double* __restrict__ v, uint64_t n, uint32_t ngroups4,
+              const double* __restrict__ pmax, const double* __restrict__ psum, uint32_t nparts,
+              VecScale* __restrict__ sc_out, uint32_t* __restrict__ out) {
+  const VecScale sc = scale_from_partials(pmax, psum, nparts);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *sc_out = sc;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // 4 consecutive elements
+  if (t >= ngroups4) return;
+  const int ex = sc.ex;
+  const bool live = sc.delta > 0.0;
+  uint32_t dig[8] = {};
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    const uint64_t i = (uint64_t)t * 4 + b;
+    long long q = 0;
+    if (live && i < n) q = __double2ll_rn(ldexp(v[i], kSliceBits - ex));
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      long long d = (s < 7) ? (((q + 64) & 127) - 64) : q;
+      q = (q - d) >> 7;
+      dig[s] |= ((uint32_t)(d & 0xFF)) << (8 * b);
+    }
+  }
+  const uint32_t grp = t >> 3, kk4 = t & 7;       // 8 groups of 4 per 32 elements
+  const uint32_t h = kk4 >> 2, q4 = kk4 & 3;      // b0 (k < 16) or b1, and lane q
+#pragma unroll
+  for (int s = 0; s < 8; s++) out[(((uint64_t)grp * 8 + s) * 4 + q4) * 2 + h] = dig[s];
+}
+
+__global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
+k_imma_gemv_tma_t(const __grid_constant__ TmaDesc tmap, uint32_t C /* output length */,
+                  const uint32_t* __restrict__ S, uint32_t ntiles, uint32_t tiles_per_split,
+                  double* __restrict__ out, uint64_t out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kTmaStages * kTmaTStageBytes;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t t_begin = blockIdx.y * tiles_per_split;
+  const uint32_t t_end = min(ntiles, t_begin + tiles_per_split);
+  const uint32_t nst = t_end > t_begin ? t_end - t_begin : 0;
+  const uint32_t xbyte0 = blockIdx.x * kTmaStageCols;
+
+  if (tid == 0) {
+    for (int i = 0; i < kTmaStages; i++) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (kTmaStages + i), kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumerWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+      for (uint32_t it = 0; it < nst; it++) {
+        const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+        const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTmaStages + slot);
+        if (round > 0) mbar_wait(empty, (round - 1) & 1);
+        const uint32_t dst = base + slot * kTmaTStageBytes;
+        mbar_expect_tx(full, kTmaTStageBytes);
+        tma_load_2d(dst, &tmap, (int)xbyte0, (int)((t_begin + it) * kTmaRows), full, pol_stream);
+        bulk_load(dst + kTmaTileBytes, S + (uint64_t)(t_begin + it) * (kTmaTSliceBytes / 4),
+                  kTmaTSliceBytes, full, pol_keep);
+      }
+    }
+    return;
+  }
+
+  const int g = lane >> 2, q = lane & 3;
+  int acc[4][4] = {};       // [field][frag]
+  double dacc[4][4] = {};
+  for (uint32_t it = 0; it < nst; it++) {
+    const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+    mbar_wait(bars + 8 * slot, round & 1);
+    const uint32_t tile = base + slot * kTmaTStageBytes;
+    const uint32_t sl = tile + kTmaTileBytes;
+#pragma unroll
+    for (int ks = 0; ks < kTmaRows / 32; ks++) {
+      const uint32_t row = (uint32_t)(ks * 32 + lane);  // lane l supplies the address of row l
+      const uint32_t addr = tile + row * 128u + ((((uint32_t)warp) ^ (row & 7u)) << 4);
+      uint32_t a0, a1, a2, a3, b0, b1;
+      asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                   : "r"(addr));
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
+                   : "=r"(b0), "=r"(b1)
+                   : "r"(sl + (uint32_t)(((ks * 8 + g) * 4 + q) * 8)));
+      mma_u8s8(acc[0], a0 & 0x03030303u, a1 & 0x03030303u, a2 & 0x03030303u, a3 & 0x03030303u, b0, b1);
+      mma_u8s8(acc[1], a0 & 0x0C0C0C0Cu, a1 & 0x0C0C0C0Cu, a2 & 0x0C0C0C0Cu, a3 & 0x0C0C0C0Cu, b0, b1);
+      mma_u8s8(acc[2], a0 & 0x30303030u, a1 & 0x30303030u, a2 & 0x30303030u, a3 & 0x30303030u, b0, b1);
+      mma_u8s8(acc[3], a0 & 0xC0C0C0C0u, a1 & 0xC0C0C0C0u, a2 & 0xC0C0C0C0u, a3 & 0xC0C0C0C0u, b0, b1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // see k_imma_gemv_tma
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8 * (kTmaStages + slot));
+    if ((it % kTmaFlushStages) == kTmaFlushStages - 1) {
+#pragma unroll
+      for (int f = 0; f < 4; f++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          dacc[f][k] += (double)acc[f][k];
+          acc[f][k] = 0;
+        }
+    }
+  }
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+  double* o = out + (uint64_t)blockIdx.y * out_stride;
+  const uint64_t byte_a = (uint64_t)xbyte0 + warp * 16 + g;  // packed byte of MMA row g; +8 for g+8
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) dacc[f][k] += (double)acc[f][k];
+    const double sf = ldexp(1.0, -2 * f);  // the field carried e * 4^f
+    double ra = (dacc[f][0] * w0 + dacc[f][1] * w1) * sf;
+    double rb = (dacc[f][2] * w0 + dacc[f][3] * w1) * sf;
+    ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+    rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+    ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+    rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+    if (q == 0) {
+      const uint64_t ia = byte_a * 4 + f, ib = (byte_a + 8) * 4 + f;
+      if (ia < C) o[ia] = ra;
+      if (ib < C) o[ib] = rb;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Sparse missing-genotype sums  out[r] = sum_{c in row r} vec[c].
 //
 // A plain CSR gather is bound by L2 sector traffic (every 8-byte read of `vec`

@@ -222,25 +222,6 @@ k_snp_stats(const uint8_t* __restrict__ gs, uint64_t nsnps, uint64_t n, uint64_t
   nmiss[j] = n3;
 }
 
-// Missing count per row of an arbitrary packed matrix (used for gi).
-__global__ void __launch_bounds__(256)
-k_row_missing(const uint8_t* __restrict__ g, uint64_t nrows, uint64_t pitch,
-              uint32_t* __restrict__ nmiss) {
-  uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (r >= nrows) return;
-  const uint4* row = reinterpret_cast<const uint4*>(g + r * pitch);
-  uint32_t nvec = (uint32_t)(pitch / 16), c = 0;
-  for (uint32_t v = lane; v < nvec; v += 32) {
-    uint4 q = ld_stream_u128(row + v);
-    c += __popc(q.x & (q.x >> 1) & 0x55555555u) + __popc(q.y & (q.y >> 1) & 0x55555555u) +
-         __popc(q.z & (q.z >> 1) & 0x55555555u) + __popc(q.w & (q.w >> 1) & 0x55555555u);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if (lane == 0) nmiss[r] = c;
-}
-
 // CSR fill: column indices of the missing entries of every row, ascending.
 // One warp per row; words are scanned in order with a warp prefix sum.
 __global__ void __launch_bounds__(256)
@@ -274,6 +255,26 @@ k_fill_missing_csr(const uint8_t* __restrict__ g, uint64_t nrows, uint64_t pitch
     }
     base += __shfl_sync(0xffffffffu, incl, 31);
   }
+}
+
+// CSR transposition helpers (staging): keys = (column << 32 | row) of every entry,
+// sorted by a stable radix sort, give the transposed lists in ascending order.
+__global__ void __launch_bounds__(256)
+k_csr_to_keys(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ colidx,
+              uint64_t nrows, uint64_t* __restrict__ keys) {
+  uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  for (uint64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32)
+    keys[k] = ((uint64_t)colidx[k] << 32) | r;
+}
+__global__ void k_keys_to_csr(const uint64_t* __restrict__ keys, uint64_t nnz,
+                              uint32_t* __restrict__ colidx, uint32_t* __restrict__ counts) {
+  uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  uint64_t key = keys[k];
+  colidx[k] = (uint32_t)key;
+  atomicAdd(counts + (key >> 32), 1u);
 }
 
 // ---------------------------------------------------------------------------

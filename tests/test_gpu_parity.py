@@ -193,6 +193,28 @@ def test_tensor_path_is_deterministic_and_default(native_lib, monkeypatch):
     assert np.isnan(op.perform_op(np.full(n, np.nan))).all()
 
 
+@pytest.mark.parametrize("variant", ["tma", "tma2", "ldg"])
+def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
+    """FPB_GEMV selects the contraction kernels: default single-copy TMA pipeline
+    (k_imma_gemv_tma + k_imma_gemv_tma_t), two-copy TMA (tma2) and the register-staged
+    LDG kernel (ldg).  All are exact integer contractions, so they must agree with
+    each other bit for bit and with the oracle to OP_RTOL."""
+    _, payload, n, p = load_fixture("hapmap3")
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    monkeypatch.delenv("FPB_GEMV", raising=False)
+    base = _mk(payload, n, p)
+    rng = np.random.default_rng(31)
+    x, v = rng.standard_normal(n), rng.standard_normal(p)
+    y0, t0, z0 = base.perform_op(x), base.crossprod(x), base.prod(v)
+    monkeypatch.setenv("FPB_GEMV", variant)
+    op = _mk(payload, n, p)
+    assert np.array_equal(op.perform_op(x), y0)
+    assert np.array_equal(op.crossprod(x), t0)
+    assert np.array_equal(op.prod(v), z0)
+    orc = O.COracle(payload, n, p)
+    assert _relerr(y0, orc.perform_op(x, 0)) <= OP_RTOL
+
+
 def test_error_paths(native_lib):
     from flashpca_b200 import Data, SVDWideOnline
     from flashpca_b200._lib import FpbError
