@@ -82,7 +82,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -230,7 +230,6 @@ def run_b200(a):
     ms_step = timed(a.steps)
     launches = lib.fpb_launch_count(op.h) - l0
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     timed(1, want_kernels=True)
     t = torch.tensor([ms_step, kms[0], kms[1], kms[2], kms[3]], dtype=torch.float64,
                      device="cuda")
@@ -249,6 +248,7 @@ def run_b200(a):
         _lib.check(lib.fpb_perform_op(op.h, x_host.data_ptr(), y_host.data_ptr()), op.h)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -258,13 +258,16 @@ def run_b200(a):
     # ---- full k=20 solve to convergence (time-to-solution, op count)
     solve = None
     if not a.no_solve:
-        barrier()
-        t0 = time.perf_counter()
-        res = op.pca(k, 2 * k + 1, 500, 1e-6)
-        barrier()
+        runs = []
+        for _ in range(2):   # first call allocates the Lanczos workspace; the second is steady state
+            barrier()
+            t0 = time.perf_counter()
+            res = op.pca(k, 2 * k + 1, 500, 1e-6)
+            barrier()
+            runs.append((time.perf_counter() - t0, op.pca_phase_seconds()))
         op_ms = op.op_times_ms()
-        ph = op.pca_phase_seconds()
-        solve = {"seconds": time.perf_counter() - t0, "iterate_seconds": ph["iterate"],
+        sec, ph = runs[1]
+        solve = {"seconds": sec, "first_call_seconds": runs[0][0], "iterate_seconds": ph["iterate"],
                  "eigenvector_assemble_seconds": ph["assemble"],
                  "eigenvector_download_seconds": ph["download"], "nops": int(res["nops"]),
                  "nconv": int(res["nconv"]), "restarts": int(res["niter"]) - 1,
@@ -296,7 +299,9 @@ def run_b200(a):
     roofline = {
         # the dominant kernel, as the bench contract defines it: algorithmic bytes of
         # the units ONE launch processes (one half = ceil(N/4) * P_local packed bytes)
-        "bound": "hbm", "kernel": "k_imma_gemv_tma (one launch per half of perform_op)",
+        "bound": "hbm",
+        "kernel": "k_imma_gemv_tma / k_imma_gemv_tma_t (one launch per half of perform_op; "
+                  "the slower of the two is reported)",
         "achieved": kern_bytes / (dom * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": kern_bytes / (dom * 1e-3) / 1e9 / peak, "traffic": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": kern_bytes,
@@ -306,8 +311,9 @@ def run_b200(a):
         "perform_op": {"algorithmic_bytes": alg_bytes / world, "ms": ms_step,
                        "achieved": op_gbs, "frac": op_gbs / peak,
                        "halves_ms": {"Xtx": k_ms[0], "Xt": k_ms[1]},
-                       "note": "2 contraction launches + 12 small kernels per op; "
-                               "single-read roofline, capped near 0.55 by the two-copy design"},
+                       "note": "2 contraction launches + 7 small kernels per op; each half "
+                               "streams the single packed copy once, so the single-read "
+                               "roofline fraction is capped near 0.55"},
     }
 
     cpu = None
@@ -317,7 +323,12 @@ def run_b200(a):
         payload = sub.bed_payload()
         sub.close()
         val, cms, threads, bs = cpu_port_run(a, payload, n, snps, steps=3, warmup=1)
+        # BASELINE.md variant A: the reference is single-threaded in practice
+        s1 = max(64, snps // 8)
+        val1, _, _, _ = cpu_port_run(a, payload[: s1 * ((n + 3) // 4)], n, s1, steps=1, warmup=1,
+                                     threads=1)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+               "single_thread_value": val1,
                "sample": "first %d of %d SNP columns x %d individuals, 3 steps after 1 warm-up, "
                          "block_size %d (--memory 2048 formula), %.0f ms per sample step"
                          % (snps, p, n, bs, cms)}
