@@ -175,6 +175,216 @@ void print_options(std::ostream& os) {
   }
 }
 
+// A failed option check: message for stderr + process exit status.
+struct UsageError {
+  std::string msg;
+  int status;
+};
+[[noreturn]] void fail(const std::string& msg) { throw UsageError{msg, EXIT_FAILURE}; }
+
+// Everything main() needs after the command line has been checked.
+struct Config {
+  int mode = MODE_PCA;
+  bool batch = false, verbose = false, debug = false, do_loadings = false, save_meansd = false;
+  int memory = 2048, n_dim = 10, maxiter = 500, precision = 7, device = 0;
+  int stand_method_x = STANDARDISE_BINOM2, divisor = DIVISOR_P;
+  unsigned int block_size = 0;
+  long seed = 1L;
+  double tol = 1e-6;
+  std::string bed, bim, fam;
+  std::map<std::string, std::string> out;  // logical output name -> file name
+  std::string in_load, in_maf, in_meansd;
+};
+
+// keyword -> code, with upstream's "unknown ..." message on a miss
+int lookup(const VarMap& vm, const char* opt, const std::map<std::string, int>& table,
+           const char* what, int dflt) {
+  if (!vm.count(opt)) return dflt;
+  auto it = table.find(vm.str(opt));
+  if (it == table.end()) fail(std::string("Error: unknown ") + what + " (--" + opt + "): " + vm.str(opt));
+  return it->second;
+}
+
+// integer option with a lower bound and upstream's message when it is violated
+long bounded(const VarMap& vm, const char* opt, long dflt, long lowest, const char* msg) {
+  if (!vm.count(opt)) return dflt;
+  long v = vm.as_long(opt);
+  if (v < lowest) fail(msg);
+  return v;
+}
+
+// The option checks of upstream flashpca.cpp:136-564, in upstream's order of
+// precedence, expressed as data where they are uniform.
+Config check_options(const VarMap& vm) {
+  Config c;
+  c.verbose = vm.count("verbose");
+  c.debug = vm.count("debug");
+
+  // -- analysis mode
+  const char* all_modes[] = {"cca", "ucca", "scca", "check", "project"};
+  auto conflicts = [&](const std::string& chosen) {
+    for (const char* other : all_modes)
+      if (chosen != other && vm.count(other))
+        fail("Error: conflicting modes requested: --" + chosen + ", --" + other +
+             "\nUse --help to get more help");
+  };
+  for (const char* gone : {"scca", "ucca"})
+    if (vm.count(gone)) {
+      conflicts(gone);
+      fail(std::string("Error: --") + gone +
+           " is not part of the B200 build (PCA, --check and --project only)");
+    }
+  if (vm.count("check")) {
+    conflicts("check");
+    c.mode = MODE_CHECK_PCA;
+  } else if (vm.count("project")) {
+    c.mode = MODE_PREDICT_PCA;
+    if (!vm.count("inload")) fail("Error: SNP-loadings must be specified using --inload");
+    if (!vm.count("inmaf") && !vm.count("inmeansd"))
+      fail("Error: one of MAF or mean/stdev must be specified using "
+           " --inmaf or --inmeansd, respectively");
+  }
+  c.batch = vm.count("batch") && c.mode == MODE_PCA;  // MEM_MODE_OFFLINE applies to PCA only
+
+  // -- sizes
+  c.memory = (int)bounded(vm, "memory", 2048, 1, "Error: memory (MB) must be >=1");
+  if (vm.count("blocksize")) {
+    if (vm.count("memory"))
+      fail("Error: cannot specify both --memory and --blocksize at the same time");
+    c.block_size = (unsigned int)bounded(vm, "blocksize", 0, 1, "Error: blocksize must be >=1");
+  }
+  if (vm.count("seed")) c.seed = vm.as_long("seed");
+
+  // -- input fileset
+  if (vm.count("bfile")) {
+    const std::string& root = vm.str("bfile");
+    c.bed = root + ".bed";
+    c.bim = root + ".bim";
+    c.fam = root + ".fam";
+  } else if (vm.count("bed") && vm.count("bim") && vm.count("fam")) {
+    c.bed = vm.str("bed");
+    c.bim = vm.str("bim");
+    c.fam = vm.str("fam");
+  } else {
+    fail("Error: you must specify either --bfile or --bed / --fam / --bim\n"
+         "Use --help to get more help");
+  }
+
+  c.n_dim = (int)bounded(vm, "ndim", 10, 1, "Error: --ndim can't be less than 1");
+  c.stand_method_x = lookup(vm, "standx", {{"binom", STANDARDISE_BINOM}, {"binom2", STANDARDISE_BINOM2}},
+                            "standardization method", STANDARDISE_BINOM2);
+
+  // -- output names: <stem><suffix> unless an explicit --out* option is given
+  const std::string suffix = vm.count("suffix") ? vm.str("suffix") : ".txt";
+  const struct { const char *key, *stem, *opt; } outs[] = {
+      {"pcs", "pcs", "outpc"},           {"eigenvectors", "eigenvectors", "outvec"},
+      {"eigenvalues", "eigenvalues", "outval"}, {"pve", "pve", "outpve"},
+      {"meansd", "meansd", "outmeansd"}, {"projection", "projection", "outproj"}};
+  for (const auto& o : outs) c.out[o.key] = vm.count(o.opt) ? vm.str(o.opt) : o.stem + suffix;
+  c.save_meansd = vm.count("outmeansd");
+  if (vm.count("outload")) {
+    c.out["loadings"] = vm.str("outload");
+    c.do_loadings = true;
+  }
+
+  // -- solver
+  c.maxiter = (int)bounded(vm, "maxiter", 500, 1, "Error: --maxiter can't be less than 1");
+  if (vm.count("tol")) {
+    c.tol = vm.as_double("tol");
+    if (c.tol <= 0) fail("Error: --tol can't be zero or negative");
+  }
+  c.divisor = lookup(vm, "div", {{"none", DIVISOR_NONE}, {"n1", DIVISOR_N1}, {"p", DIVISOR_P}},
+                     "divisor", DIVISOR_P);
+
+  // -- projection inputs
+  if (vm.count("inmeansd") && vm.count("inmaf"))
+    fail("Error: conflicting options requested --inmeansd, --inmaf");
+  for (const auto& in : {std::make_pair("inmeansd", &c.in_meansd), std::make_pair("inmaf", &c.in_maf),
+                         std::make_pair("inload", &c.in_load)}) {
+    if (!vm.count(in.first)) continue;
+    *in.second = vm.str(in.first);
+    if (in.second->empty()) fail(std::string("Error: no file specified for --") + in.first);
+  }
+
+  c.precision = (int)bounded(vm, "precision", 7, 2, "Error: output --precision too low");
+  if (vm.count("device")) c.device = (int)vm.as_long("device");
+  return c;
+}
+
+// --memory (MB) -> number of SNPs per block, upstream flashpca.cpp:636-688.  The
+// value only feeds the "blocksize" log line: the genotypes are resident in HBM.
+unsigned int block_size_from_memory(const Config& c, const Data& data) {
+  const long long n = data.N, p = data.nsnps, k = c.n_dim;
+  const long long reserve = 2 * p * 8 * 2            // avg + stdev
+                            + 3 * p * 8              // genotype table
+                            + n * k * 8              // U
+                            + (c.do_loadings ? p * k * 8 : 0)  // V
+                            + 2 * n                  // PLINK buffers
+                            + 2 * (n + p) * k * 8    // solver workspace
+                            + 2 * 1024 * 1024 + n * 8;
+  const long long budget = (long long)c.memory * 1048576, left = budget - reserve;
+  if (c.verbose)
+    std::cout << timestamp() << "mem: " << budget << " mem_req_bytes: " << reserve
+              << " mem_remain_bytes: " << left << std::endl;
+  if (left <= 0)
+    fail("The memory specified using --memory is not sufficient, try increasing it to at least " +
+         std::to_string((reserve + n * 8) / 1048576) + " MB");
+  unsigned int bs = (unsigned int)floor(left / ((double)n * 8.0));
+  if (bs < 1) fail("The memory specified using --memory is not sufficient, try increasing it");
+  return bs;
+}
+
+std::vector<std::string> paired(const std::vector<std::string>& a, const std::vector<std::string>& b) {
+  std::vector<std::string> r(a.size());
+  for (size_t i = 0; i < a.size(); i++) r[i] = a[i] + TXT_SEP + b[i];
+  return r;
+}
+std::vector<std::string> numbered(const std::string& first, const std::string& prefix, size_t n) {
+  std::vector<std::string> r{first};
+  for (size_t i = 1; i <= n; i++) r.push_back(prefix + std::to_string(i));
+  return r;
+}
+
+// Result files of upstream flashpca.cpp:755-878.
+void write_outputs(const Config& c, const Data& data, RandomPCA& rpca) {
+  const std::vector<std::string> none;
+  const std::string idhdr = std::string("FID") + TXT_SEP + "IID";
+  const std::string snphdr = std::string("SNP") + TXT_SEP + "RefAllele";
+  auto announce = [&](const std::string& what, const std::string& file) {
+    std::cout << timestamp() << "Writing " << what << " to file " << file << std::endl;
+  };
+  const std::string k = std::to_string(c.n_dim);
+  if (c.mode == MODE_PCA) {
+    const std::vector<std::string> people = paired(data.fam_ids, data.indiv_ids);
+    announce(k + " eigenvalues", c.out.at("eigenvalues"));
+    save_text(rpca.d, none, none, c.out.at("eigenvalues").c_str(), c.precision);
+    announce(k + " eigenvectors", c.out.at("eigenvectors"));
+    save_text(rpca.U, numbered(idhdr, "U", rpca.U.cols()), people, c.out.at("eigenvectors").c_str(),
+              c.precision);
+    announce(k + " PCs", c.out.at("pcs"));
+    save_text(rpca.Px, numbered(idhdr, "PC", rpca.Px.cols()), people, c.out.at("pcs").c_str(),
+              c.precision);
+    announce(k + " proportion variance explained", c.out.at("pve"));
+    save_text(rpca.pve, none, none, c.out.at("pve").c_str(), c.precision);
+    if (c.do_loadings) {
+      std::cout << timestamp() << "Writing SNP loadings to file " << c.out.at("loadings") << std::endl;
+      save_text(rpca.V, numbered(snphdr, "V", rpca.V.cols()), paired(data.snp_ids, data.ref_alleles),
+                c.out.at("loadings").c_str(), c.precision);
+    }
+  } else if (c.mode == MODE_PREDICT_PCA) {
+    save_text(rpca.Px, numbered(idhdr, "PC", rpca.Px.cols()), paired(data.fam_ids, data.indiv_ids),
+              c.out.at("projection").c_str(), c.precision);
+  } else {
+    std::cout << timestamp() << "Mean squared error: " << rpca.mse
+              << ", Root mean squared error: " << rpca.rmse << " (n=" << data.N << ")" << std::endl;
+  }
+  if (c.save_meansd) {
+    std::cout << timestamp() << "Writing mean + sd file " << c.out.at("meansd") << std::endl;
+    save_text(rpca.X_meansd, {snphdr, "Mean", "SD"}, paired(data.snp_ids, data.ref_alleles),
+              c.out.at("meansd").c_str(), c.precision);
+  }
+}
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
@@ -182,362 +392,83 @@ int main(int argc, char* argv[]) {
   try {
     parse_command_line(argc, argv, vm);
   } catch (std::exception& e) {
+    // upstream reports a malformed command line and still exits with success (flashpca.cpp:100-105)
     std::cerr << e.what() << std::endl << "Use --help to get more help" << std::endl;
-    return EXIT_SUCCESS;  // as upstream (flashpca.cpp:100-105)
+    return EXIT_SUCCESS;
   }
-
   show_timestamp = !vm.count("notime");
-  bool verbose = vm.count("verbose");
 
   std::cout << timestamp() << "arguments: flashpca ";
   for (int i = 0; i < argc; i++) std::cout << argv[i] << " ";
   std::cout << std::endl;
 
-  if (vm.count("version")) {
+  if (vm.count("version") || vm.count("help")) {
     std::cerr << "flashpca " << VERSION << std::endl;
-    std::cerr << "B200-native build of the FlashPCA2 PCA path." << std::endl
-              << "This is free software; see the source for copying conditions.  There is NO"
-              << std::endl
-              << "warranty; not even for MERCHANTABILITY or FITNESS FOR A PARTICULAR PURPOSE."
-              << std::endl
-              << std::endl;
-    return EXIT_SUCCESS;
-  }
-  if (vm.count("help")) {
-    std::cerr << "flashpca " << VERSION << std::endl;
-    print_options(std::cerr);
+    if (vm.count("help")) print_options(std::cerr);
+    else
+      std::cerr << "B200-native build of the FlashPCA2 PCA path." << std::endl
+                << "This is free software; see the source for copying conditions.  There is NO"
+                << std::endl
+                << "warranty; not even for MERCHANTABILITY or FITNESS FOR A PARTICULAR PURPOSE."
+                << std::endl << std::endl;
     return EXIT_SUCCESS;
   }
 
   try {
-    // ---- mode selection (flashpca.cpp:136-228)
-    int mode = MODE_PCA;
-    const std::vector<std::string> modes = {"cca", "ucca", "scca", "check", "project"};
-    for (const char* unsupported : {"scca", "ucca"}) {
-      if (vm.count(unsupported)) {
-        for (const std::string& m : modes)
-          if (m != unsupported && vm.count(m)) {
-            std::cerr << "Error: conflicting modes requested: --" << unsupported << ", --" << m
-                      << std::endl << "Use --help to get more help" << std::endl;
-            return EXIT_FAILURE;
-          }
-        std::cerr << "Error: --" << unsupported
-                  << " is not part of the B200 build (PCA, --check and --project only)"
-                  << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    if (vm.count("check")) {
-      if (vm.count("project")) {
-        std::cerr << "Error: conflicting modes requested: --check, --project" << std::endl
-                  << "Use --help to get more help" << std::endl;
-        return EXIT_FAILURE;
-      }
-      mode = MODE_CHECK_PCA;
-    } else if (vm.count("project")) {
-      mode = MODE_PREDICT_PCA;
-      if (!vm.count("inload")) {
-        std::cerr << "Error: SNP-loadings must be specified using --inload" << std::endl;
-        return EXIT_FAILURE;
-      }
-      if (!vm.count("inmaf") && !vm.count("inmeansd")) {
-        std::cerr << "Error: one of MAF or mean/stdev must be specified using "
-                  << " --inmaf or --inmeansd, respectively" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    // --batch: all genotypes as doubles (flashpca.cpp:229-234, MEM_MODE_OFFLINE)
-    bool batch = vm.count("batch") && mode == MODE_PCA;
-
-    int memory = 2048;
-    if (vm.count("memory")) {
-      memory = (int)vm.as_long("memory");
-      if (memory < 1) {
-        std::cerr << "Error: memory (MB) must be >=1" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    unsigned int block_size = 0;
-    if (vm.count("blocksize")) {
-      if (vm.count("memory")) {
-        std::cerr << "Error: cannot specify both --memory and --blocksize"
-                  << " at the same time" << std::endl;
-        return EXIT_FAILURE;
-      }
-      long bs = vm.as_long("blocksize");
-      if (bs < 1) {
-        std::cerr << "Error: blocksize must be >=1" << std::endl;
-        return EXIT_FAILURE;
-      }
-      block_size = (unsigned int)bs;
-    }
-    long seed = 1L;
-    if (vm.count("seed")) seed = vm.as_long("seed");
-
-    std::string fam_file, geno_file, bim_file;
-    if (vm.count("bfile")) {
-      geno_file = vm.str("bfile") + std::string(".bed");
-      bim_file = vm.str("bfile") + std::string(".bim");
-      fam_file = vm.str("bfile") + std::string(".fam");
-    } else {
-      bool good = true;
-      if (vm.count("bed")) geno_file = vm.str("bed");
-      else good = false;
-      if (good && vm.count("bim")) bim_file = vm.str("bim");
-      else good = false;
-      if (good && vm.count("fam")) fam_file = vm.str("fam");
-      else good = false;
-      if (!good) {
-        std::cerr << "Error: you must specify either --bfile "
-                  << "or --bed / --fam / --bim" << std::endl
-                  << "Use --help to get more help" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-
-    int n_dim = 10;
-    if (vm.count("ndim")) {
-      n_dim = (int)vm.as_long("ndim");
-      if (n_dim < 1) {
-        std::cerr << "Error: --ndim can't be less than 1" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-
-    int stand_method_x = STANDARDISE_BINOM2;
-    if (vm.count("standx")) {
-      std::string m = vm.str("standx");
-      if (m == "binom") stand_method_x = STANDARDISE_BINOM;
-      else if (m == "binom2") stand_method_x = STANDARDISE_BINOM2;
-      else {
-        std::cerr << "Error: unknown standardization method (--standx): " << m << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-
-    std::string suffix = ".txt";
-    if (vm.count("suffix")) suffix = vm.str("suffix");
-    std::string pcfile = "pcs" + suffix;
-    if (vm.count("outpc")) pcfile = vm.str("outpc");
-    std::string eigvecfile = "eigenvectors" + suffix;
-    if (vm.count("outvec")) eigvecfile = vm.str("outvec");
-    std::string eigvalfile = "eigenvalues" + suffix;
-    if (vm.count("outval")) eigvalfile = vm.str("outval");
-    std::string eigpvefile = "pve" + suffix;
-    if (vm.count("outpve")) eigpvefile = vm.str("outpve");
-    std::string meansdfile = "meansd" + suffix;
-    bool save_meansd = false;
-    if (vm.count("outmeansd")) {
-      meansdfile = vm.str("outmeansd");
-      save_meansd = true;
-    }
-    std::string projfile = "projection" + suffix;
-    if (vm.count("outproj")) projfile = vm.str("outproj");
-
-    int maxiter = 500;
-    bool debug = vm.count("debug");
-    if (vm.count("maxiter")) {
-      maxiter = (int)vm.as_long("maxiter");
-      if (maxiter <= 0) {
-        std::cerr << "Error: --maxiter can't be less than 1" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    double tol = 1e-6;
-    if (vm.count("tol")) {
-      tol = vm.as_double("tol");
-      if (tol <= 0) {
-        std::cerr << "Error: --tol can't be zero or negative" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    bool do_loadings = false;
-    std::string loadingsfile = "";
-    if (vm.count("outload")) {
-      loadingsfile = vm.str("outload");
-      do_loadings = true;
-    }
-    int divisor = DIVISOR_P;
-    if (vm.count("div")) {
-      std::string m = vm.str("div");
-      if (m == "none") divisor = DIVISOR_NONE;
-      else if (m == "n1") divisor = DIVISOR_N1;
-      else if (m == "p") divisor = DIVISOR_P;
-      else {
-        std::cerr << "Error: unknown divisor (--div): " << m << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    std::string in_meansd_file = "", in_maf_file = "";
-    if (vm.count("inmeansd")) {
-      if (vm.count("inmaf")) {
-        std::cerr << "Error: conflicting options requested --inmeansd, --inmaf" << std::endl;
-        return EXIT_FAILURE;
-      }
-      in_meansd_file = vm.str("inmeansd");
-      if (in_meansd_file == "") {
-        std::cerr << "Error: no file specified for --inmeansd" << std::endl;
-        return EXIT_FAILURE;
-      }
-    } else if (vm.count("inmaf")) {
-      in_maf_file = vm.str("inmaf");
-      if (in_maf_file == "") {
-        std::cerr << "Error: no file specified for --inmaf" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    std::string in_load_file = "";
-    if (vm.count("inload")) {
-      in_load_file = vm.str("inload");
-      if (in_load_file == "") {
-        std::cerr << "Error: no file specified for --inload" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    int precision = 7;
-    if (vm.count("precision")) {
-      precision = (int)vm.as_long("precision");
-      if (precision <= 1) {
-        std::cerr << "Error: output --precision too low" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
-    int device = 0;
-    if (vm.count("device")) device = (int)vm.as_long("device");
-
-    // ---- end of command line parsing
+    const Config c = check_options(vm);
     std::cout << timestamp() << "Start flashpca (version " << VERSION << ")" << std::endl;
 
     Data data;
-    data.verbose = verbose;
-    data.stand_method_x = stand_method_x;
-    verbose&& std::cout << timestamp() << "seed: " << seed << std::endl;
-
-    data.read_pheno(fam_file.c_str(), 6);
-    data.read_plink_bim(bim_file.c_str());
-    data.read_plink_fam(fam_file.c_str());
-    data.geno_filename = geno_file;
+    data.verbose = c.verbose;
+    data.stand_method_x = c.stand_method_x;
+    if (c.verbose) std::cout << timestamp() << "seed: " << c.seed << std::endl;
+    data.read_pheno(c.fam.c_str(), 6);  // N = number of fam lines; column 6 must be numeric
+    data.read_plink_bim(c.bim.c_str());
+    data.read_plink_fam(c.fam.c_str());
+    data.geno_filename = c.bed;
     data.get_size();
     data.prepare();
-    if (batch) data.read_bed(false);  // flashpca.cpp:597-601
+    if (c.batch) data.read_bed(false);
 
     RandomPCA rpca;
-    rpca.verbose = verbose;
-    rpca.debug = debug;
-    rpca.stand_method_x = stand_method_x;
-    rpca.divisor = divisor;
-    rpca.device = device;
+    rpca.verbose = c.verbose;
+    rpca.debug = c.debug;
+    rpca.stand_method_x = c.stand_method_x;
+    rpca.divisor = c.divisor;
+    rpca.device = c.device;
 
-    // ncv = 2*ndim+1 --> ndim < (n-1)/2   (flashpca.cpp:623-633)
-    unsigned int max_dim = (unsigned int)((fminl(data.N, data.nsnps) - 1) / 2.0);
-    if ((unsigned int)n_dim > max_dim) {
-      std::cerr << "Error: You asked for " << n_dim << " dimensions, but only " << max_dim
-                << "allowed" << std::endl;
-      return EXIT_FAILURE;
-    }
+    // ncv = 2*ndim+1 must stay below min(N, p): ndim <= (min(N, p) - 1) / 2
+    const unsigned int max_dim = (unsigned int)((fminl(data.N, data.nsnps) - 1) / 2.0);
+    if ((unsigned int)c.n_dim > max_dim)
+      fail("Error: You asked for " + std::to_string(c.n_dim) + " dimensions, but only " +
+           std::to_string(max_dim) + "allowed");
 
-    // --memory -> block_size (flashpca.cpp:636-688).  The value only feeds the
-    // log line below: the genotypes are resident in HBM, not re-read in blocks.
-    long long mem = (long long)memory * 1048576;
-    if (block_size == 0) {
-      long long mem_req_bytes = 2 * (long long)data.nsnps * 8 * 2 + 3 * (long long)data.nsnps * 8 +
-                                (long long)data.N * n_dim * 8 +
-                                (do_loadings ? (long long)data.nsnps * n_dim * 8 : 0) +
-                                2 * (long long)data.N +
-                                2 * (long long)(data.N + data.nsnps) * n_dim * 8 +
-                                2 * 1024 * 1024 + (long long)data.N * 8;
-      long long mem_remain_bytes = mem - mem_req_bytes;
-      verbose&& std::cout << timestamp() << "mem: " << mem << " mem_req_bytes: " << mem_req_bytes
-                          << " mem_remain_bytes: " << mem_remain_bytes << std::endl;
-      if (mem_remain_bytes <= 0) {
-        std::cerr << "The memory specified using --memory is not sufficient, try"
-                  << " increasing it to at least " << (mem_req_bytes + data.N * 8) / 1048576
-                  << " MB" << std::endl;
-        return EXIT_FAILURE;
-      }
-      block_size = (unsigned int)floor(mem_remain_bytes / ((double)data.N * 8.0));
-      if (block_size < 1) {
-        std::cerr << "The memory specified using --memory is not sufficient, try"
-                  << " increasing it" << std::endl;
-        return EXIT_FAILURE;
-      }
-    }
+    unsigned int block_size = c.block_size ? c.block_size : block_size_from_memory(c, data);
     block_size = (unsigned int)fminl(block_size, data.nsnps);
     std::cout << timestamp() << "blocksize: " << block_size << " ("
               << (long long)block_size * 8 * data.N << " bytes per block)" << std::endl;
 
-    // ---- the main analysis
-    if (mode == MODE_PCA) {
-      std::cout << timestamp() << "PCA begin" << std::endl;
-      if (batch) rpca.pca_fast(data.X, block_size, n_dim, maxiter, tol, seed, do_loadings);
-      else rpca.pca_fast(data, block_size, n_dim, maxiter, tol, seed, do_loadings);
-      std::cout << timestamp() << "PCA done" << std::endl;
-    } else if (mode == MODE_CHECK_PCA) {
-      rpca.check(data, block_size, eigvecfile, eigvalfile);
-    } else if (mode == MODE_PREDICT_PCA) {
-      rpca.project(data, block_size, in_load_file, in_maf_file, in_meansd_file);
+    switch (c.mode) {
+      case MODE_PCA:
+        std::cout << timestamp() << "PCA begin" << std::endl;
+        if (c.batch)
+          rpca.pca_fast(data.X, block_size, c.n_dim, c.maxiter, c.tol, c.seed, c.do_loadings);
+        else
+          rpca.pca_fast(data, block_size, c.n_dim, c.maxiter, c.tol, c.seed, c.do_loadings);
+        std::cout << timestamp() << "PCA done" << std::endl;
+        break;
+      case MODE_CHECK_PCA:
+        rpca.check(data, block_size, c.out.at("eigenvectors"), c.out.at("eigenvalues"));
+        break;
+      case MODE_PREDICT_PCA:
+        rpca.project(data, block_size, c.in_load, c.in_maf, c.in_meansd);
+        break;
     }
-
-    // ---- write out results (flashpca.cpp:755-878)
-    const std::vector<std::string> none;
-    if (mode == MODE_PCA) {
-      std::cout << timestamp() << "Writing " << n_dim << " eigenvalues to file " << eigvalfile
-                << std::endl;
-      save_text(rpca.d, none, none, eigvalfile.c_str(), precision);
-
-      std::cout << timestamp() << "Writing " << n_dim << " eigenvectors to file " << eigvecfile
-                << std::endl;
-      std::vector<std::string> rownames(rpca.Px.rows());
-      for (size_t i = 0; i < rpca.Px.rows(); i++)
-        rownames[i] = data.fam_ids[i] + TXT_SEP + data.indiv_ids[i];
-      std::vector<std::string> colnames(rpca.Px.cols() + 1);
-      colnames[0] = std::string("FID") + TXT_SEP + "IID";
-      for (size_t i = 0; i < rpca.Px.cols(); i++) colnames[i + 1] = "U" + std::to_string(i + 1);
-      save_text(rpca.U, colnames, rownames, eigvecfile.c_str(), precision);
-
-      std::cout << timestamp() << "Writing " << n_dim << " PCs to file " << pcfile << std::endl;
-      for (size_t i = 0; i < rpca.Px.cols(); i++) colnames[i + 1] = "PC" + std::to_string(i + 1);
-      save_text(rpca.Px, colnames, rownames, pcfile.c_str(), precision);
-
-      std::cout << timestamp() << "Writing " << n_dim << " proportion variance explained to file "
-                << eigpvefile << std::endl;
-      save_text(rpca.pve, none, none, eigpvefile.c_str(), precision);
-
-      if (do_loadings) {
-        std::cout << timestamp() << "Writing"
-                  << " SNP loadings to file " << loadingsfile << std::endl;
-        std::vector<std::string> lcol = {std::string("SNP") + TXT_SEP + "RefAllele"};
-        for (size_t i = 0; i < rpca.V.cols(); i++)
-          lcol.push_back(std::string("V") + std::to_string(i + 1));
-        std::vector<std::string> lrow(data.snp_ids.size());
-        for (size_t i = 0; i < lrow.size(); i++)
-          lrow[i] = data.snp_ids[i] + TXT_SEP + data.ref_alleles[i];
-        save_text(rpca.V, lcol, lrow, loadingsfile.c_str(), precision);
-      }
-    } else if (mode == MODE_PREDICT_PCA) {
-      std::vector<std::string> rownames(rpca.Px.rows());
-      for (size_t i = 0; i < rpca.Px.rows(); i++)
-        rownames[i] = data.fam_ids[i] + TXT_SEP + data.indiv_ids[i];
-      std::vector<std::string> colnames(rpca.Px.cols() + 1);
-      colnames[0] = std::string("FID") + TXT_SEP + "IID";
-      for (size_t i = 0; i < rpca.Px.cols(); i++) colnames[i + 1] = "PC" + std::to_string(i + 1);
-      save_text(rpca.Px, colnames, rownames, projfile.c_str(), precision);
-    } else if (mode == MODE_CHECK_PCA) {
-      std::cout << timestamp() << "Mean squared error: " << rpca.mse
-                << ", Root mean squared error: " << rpca.rmse << " (n=" << data.N << ")"
-                << std::endl;
-    }
-
-    if (save_meansd) {
-      std::cout << timestamp() << "Writing mean + sd file " << meansdfile << std::endl;
-      std::vector<std::string> v = {std::string("SNP") + TXT_SEP + "RefAllele", "Mean", "SD"};
-      std::vector<std::string> rownames(data.snp_ids.size());
-      for (size_t i = 0; i < rownames.size(); i++)
-        rownames[i] = data.snp_ids[i] + TXT_SEP + data.ref_alleles[i];
-      save_text(rpca.X_meansd, v, rownames, meansdfile.c_str(), precision);
-    }
-
+    write_outputs(c, data, rpca);
     std::cout << timestamp() << "Goodbye!" << std::endl;
+  } catch (UsageError& u) {
+    std::cerr << u.msg << std::endl;
+    return u.status;
   } catch (std::exception& e) {
     std::cerr << timestamp() << "Exception: " << e.what() << std::endl;
     std::cerr << timestamp() << "Terminating" << std::endl;
