@@ -409,3 +409,38 @@ def test_in_memory_matrix_path(native_lib, method):
     if method in (2, 3):  # the bed path and the matrix path agree (test_pca.R:108-131)
         opb = _mk(payload, n, p, stand_method=method)
         assert _relerr(opb.perform_op(v), y_ref) <= 1e-11
+
+
+def test_random_matrices_vs_oracle(native_lib, monkeypatch):
+    """Seeded sweep over shapes, missing rates, standardisation methods and both
+    compute paths: statistics bit-exact, operator family within OP_RTOL."""
+    rng = np.random.default_rng(20240607)
+    for case in range(40):
+        n = int(rng.integers(1, 700))
+        p = int(rng.integers(1, 400))
+        miss = float(rng.choice([0.0, 0.002, 0.05, 0.5]))
+        stand = int(rng.choice([O.STANDARDISE_BINOM, O.STANDARDISE_BINOM2]))
+        path = ["imma", "generic"][case % 2]
+        maf = rng.uniform(0.0, 0.5, size=p)          # includes near-monomorphic SNPs
+        g = rng.binomial(2, maf[None, :], size=(n, p))
+        codes = np.where(g == 2, 0, np.where(g == 1, 2, 3)).astype(np.uint8)
+        codes[rng.random((n, p)) < miss] = 1
+        payload = _pack(codes)
+        monkeypatch.setenv("FPB_PATH", path)
+        op = _mk(payload, n, p, stand_method=stand)
+        orc = O.COracle(payload, n, p, stand)
+        x = rng.standard_normal(n)
+        v = rng.standard_normal(p)
+        y_ref = orc.perform_op(x, 0)
+        tag = "case %d: n=%d p=%d miss=%g stand=%d path=%s" % (case, n, p, miss, stand, path)
+        got, want = op.meansd(), orc.meansd()
+        assert np.array_equal(np.isnan(got), np.isnan(want)), tag
+        assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), tag
+        scale = max(np.abs(y_ref).max(), 1e-30)
+        assert np.abs(op.perform_op(x) - y_ref).max() <= OP_RTOL * max(scale, 1.0), tag
+        t_ref = orc.crossprod(x)
+        assert np.abs(op.crossprod(x) - t_ref).max() <= OP_RTOL * max(np.abs(t_ref).max(), 1.0), tag
+        z_ref = orc.prod(v)
+        assert np.abs(op.prod(v) - z_ref).max() <= OP_RTOL * max(np.abs(z_ref).max(), 1.0), tag
+        assert abs(op.trace - orc.trace) <= 1e-12 * max(orc.trace, 1.0), tag
+        op.close()
