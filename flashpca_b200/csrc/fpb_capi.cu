@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -346,14 +347,45 @@ int transpose_csr(fpb_handle* h, uint64_t rows_in, uint64_t rows_out, const uint
   return 0;
 }
 
+// Column/row splits of a TMA contraction grid (1 CTA per SM resident).  With
+// `units` independent tiles and `nstages` pipeline stages to divide per tile, a
+// split count s gives units*s CTAs of ceil(nstages/s) stages each; the kernel
+// takes about ceil(units*s / SMs) rounds of (stages + pipeline fill).  Pick the s
+// that minimises that estimate (keeps the last round full and the fill amortised).
+void pick_splits_waves(uint32_t units, uint32_t nstages, int sm_count, uint32_t* splits,
+                       uint32_t* per_split) {
+  const double fill = 4.0;  // pipeline fill + epilogue of a CTA, in stage times (~3 us / 0.7 us)
+  uint32_t best = 1;
+  double best_cost = 1e300;
+  const uint32_t smax = std::max<uint32_t>(1, std::min<uint32_t>(64, nstages / 8));
+  for (uint32_t sp = 1; sp <= smax; sp++) {
+    const uint32_t per = (nstages + sp - 1) / sp;
+    const uint32_t real = (nstages + per - 1) / per;  // splits actually launched
+    const double rounds = std::ceil((double)units * real / sm_count);
+    const double cost = rounds * (per + fill);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  *per_split = (nstages + best - 1) / best;
+  *splits = (nstages + *per_split - 1) / *per_split;
+}
+
+// debug: FPB_DEBUG_SPLITS1 / FPB_DEBUG_SPLITS2 override the split count of the first /
+// second contraction kernel (tuning sweeps)
+void override_splits(const char* env, uint32_t nstages, uint32_t* splits, uint32_t* per_split) {
+  const char* v = getenv(env);
+  if (!v) return;
+  uint32_t sp = (uint32_t)std::max(1, atoi(v));
+  sp = std::min<uint32_t>(sp, nstages);
+  *per_split = (nstages + sp - 1) / sp;
+  *splits = (nstages + *per_split - 1) / *per_split;
+}
+
 void pick_splits_tma(uint32_t rows, uint32_t nstages, int sm_count, uint32_t* splits,
                      uint32_t* sps) {
-  uint32_t tiles = (rows + fpb::kTmaRows - 1) / fpb::kTmaRows;
-  uint32_t want = (20u * sm_count + tiles - 1) / tiles;  // 1 CTA per SM resident
-  uint32_t s = std::min<uint32_t>(want, std::max<uint32_t>(1, nstages / 32));
-  s = std::max<uint32_t>(1, std::min<uint32_t>(s, 64));
-  *sps = (nstages + s - 1) / s;
-  *splits = (nstages + *sps - 1) / *sps;
+  pick_splits_waves((rows + fpb::kTmaRows - 1) / fpb::kTmaRows, nstages, sm_count, splits, sps);
 }
 
 // 2-D uint8 tensor map over a packed matrix: dim0 = bytes of a row, dim1 = rows;
@@ -492,15 +524,20 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
     h->nstages_s = (uint32_t)((h->pitch_s + fpb::kTmaStageCols - 1) / fpb::kTmaStageCols);
     h->nstages_i = (uint32_t)((h->pitch_i + fpb::kTmaStageCols - 1) / fpb::kTmaStageCols);
     pick_splits_tma((uint32_t)h->nsnps, h->nstages_s, h->sm_count, &h->tsplits_s, &h->sps_s);
+    override_splits("FPB_DEBUG_SPLITS1", h->nstages_s, &h->tsplits_s, &h->sps_s);
     pick_splits_tma((uint32_t)h->n, h->nstages_i, h->sm_count, &h->tsplits_i, &h->sps_i);
     if (h->single_copy) {
       // second half over gs: CTAs = 128-byte column stripes x splits of the 256-row tiles
       h->ttiles = (uint32_t)((h->nsnps + fpb::kTmaRows - 1) / fpb::kTmaRows);
-      uint32_t stripes = h->nstages_s;
-      uint32_t want = (20u * h->sm_count + stripes - 1) / stripes;
-      uint32_t sp = std::max<uint32_t>(1, std::min<uint32_t>(want, std::max<uint32_t>(1, h->ttiles / 16)));
+      // measured (tools/sweep_splits.sh, 500k x 100k): the column-stripe kernel is fastest with
+      // ~48 row tiles per CTA (8 splits: 1.87 ms vs 1.92 at 3 and 2.01 at 24); few stripes
+      // (small N) need more splits to occupy every SM
+      uint32_t sp = std::max<uint32_t>((h->ttiles + 24) / 48,
+                                       (h->sm_count + h->nstages_s - 1) / h->nstages_s);
+      sp = std::max<uint32_t>(1, std::min<uint32_t>(sp, std::min<uint32_t>(64, std::max<uint32_t>(1, h->ttiles / 8))));
       h->ttps = (h->ttiles + sp - 1) / sp;
       h->ttsplits = (h->ttiles + h->ttps - 1) / h->ttps;
+      override_splits("FPB_DEBUG_SPLITS2", h->ttiles, &h->ttsplits, &h->ttps);
     }
     if (h->use_tma) {
       if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_s)) return 1;
@@ -685,12 +722,14 @@ void join_gather(fpb_handle* h) { cudaStreamWaitEvent(h->stream, h->ev_join, 0);
 
 // first half: t = X'x (d_t) and/or the a, corr inputs of the second half
 void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_half) {
+  static const bool gather_after = getenv("FPB_DEBUG_GATHER_AFTER") != nullptr;
   if (h->nmissing) {
     fork_mark(h);
-    gather_launch(h, true, d_x);
+    if (!gather_after) gather_launch(h, true, d_x);
   }
   vec_partials(h, d_x, h->n);
   const uint32_t nsplits = imma_contract(h, true, d_x, h->n, 0);
+  if (h->nmissing && gather_after) gather_launch(h, true, d_x);
   if (h->nmissing) join_gather(h);
   uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
   fpb::k_finalize_crossprod<<<gb, 256, 0, h->stream>>>(
@@ -703,11 +742,13 @@ void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_h
 
 // second half from a, corr and the (max|a|, sum b) partials already in the handle
 void imma_prod_tail(fpb_handle* h, double* d_y) {
+  static const bool gather_after = getenv("FPB_DEBUG_GATHER_AFTER") != nullptr;
   if (h->nmissing) {
     fork_mark(h);
-    gather_launch(h, false, h->d_corr);
+    if (!gather_after) gather_launch(h, false, h->d_corr);
   }
   const uint32_t nsplits = imma_contract(h, false, h->d_a, h->nsnps, 1);
+  if (h->nmissing && gather_after) gather_launch(h, false, h->d_corr);
   if (h->nmissing) join_gather(h);
   uint32_t gb = (uint32_t)((h->n + 255) / 256);
   fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, nsplits, h->part_stride, h->n,

