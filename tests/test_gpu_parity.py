@@ -447,3 +447,21 @@ def test_random_matrices_vs_oracle(native_lib, monkeypatch):
         assert np.abs(op.prod(v) - z_ref).max() <= OP_RTOL * max(np.abs(z_ref).max(), 1.0), tag
         assert abs(op.trace - orc.trace) <= 1e-12 * max(orc.trace, 1.0), tag
         op.close()
+
+
+def test_pca_ndim50_like_the_r_tests(native_lib):
+    """flashpcaR's test_pca.R:3-6 asks for ndim = 50 on the 957 x 1129 fixture
+    (ncv = 101: the solver's generic, non-register-cached kernels)."""
+    from flashpca_b200 import RandomPCA
+    _, payload, n, p = load_fixture("data_chr1")
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, 50)
+    op = _mk(payload, n, p)
+    r = RandomPCA()
+    r.pca_fast(None, 0, 50, 500, 1e-6, op=op)
+    assert np.abs(r.d / ref["d"] - 1).max() < 1e-6          # test_pca.R uses tol 1e-4
+    assert np.abs(r.pve / ref["pve"] - 1).max() < 1e-6
+    # |cor| of each PC with the dense one ~ 1 (test_pca.R:24-43)
+    for j in range(50):
+        c = abs(np.corrcoef(r.Px[:, j], ref["Px"][:, j])[0, 1])
+        assert c > 1 - 1e-6, (j, c)
