@@ -52,7 +52,11 @@ SIGNATURES = {
     "fpb_pca_phase_times": (None, [_vp, _vp]),
     "fpb_time_perform_op": (_i, [_vp, _vp, _vp, _u32, _c.POINTER(_c.c_float), _vp]),
     "fpb_launch_count": (_u64, [_vp]),
+    "fpb_path_info": (_c.c_uint, [_vp]),
 }
+
+# fpb_path_info bits (include/flashpca_b200.h)
+PATH_DENSE, PATH_TENSOR, PATH_TMA, PATH_SINGLE_COPY, PATH_FUSED = 1, 2, 4, 8, 16
 
 _lib = None
 

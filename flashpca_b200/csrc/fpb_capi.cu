@@ -31,6 +31,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fpb_dense.cuh"
+#include "fpb_fused.cuh"
 #include "fpb_imma.cuh"
 #include "fpb_irlm.cuh"
 #include "fpb_kernels.cuh"
@@ -131,6 +132,13 @@ struct fpb_handle {
   bool single_copy = false;
   uint32_t ttiles = 0, ttsplits = 1, ttps = 1;
   uint64_t part_stride = 0;
+  // fused single-pass perform_op (fpb_fused.cuh)
+  bool use_fused = false;
+  fpb::TmaDesc tm_f;                       // box 128 B x kFRows rows over gs
+  uint32_t f_grid = 0, f_nslabs = 0, f_nstripes = 0, f_gpad = 0, f_window = 3, f_pol1 = 0, f_pol2 = 1;
+  double *d_fpart = nullptr, *d_ybuf = nullptr;
+  uint32_t* d_fsync = nullptr;             // cnt[nslabs], cnt2[nslabs], err
+  bool fused_used = false;                 // an op ran through the fused kernel since the last check
   // host-pointer API staging (grown on demand)
   double* d_in = nullptr;
   double* d_out = nullptr;
@@ -389,9 +397,9 @@ void pick_splits_tma(uint32_t rows, uint32_t nstages, int sm_count, uint32_t* sp
 }
 
 // 2-D uint8 tensor map over a packed matrix: dim0 = bytes of a row, dim1 = rows;
-// box = 128 B x 256 rows, 128-byte swizzle, out-of-bounds filled with zeros.
+// box = 128 B x box_rows rows, 128-byte swizzle, out-of-bounds filled with zeros.
 int make_tensor_map(fpb_handle* h, const uint8_t* base, uint64_t pitch, uint64_t rows,
-                    fpb::TmaDesc* out) {
+                    fpb::TmaDesc* out, uint32_t box_rows = fpb::kTmaRows) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -408,7 +416,7 @@ int make_tensor_map(fpb_handle* h, const uint8_t* base, uint64_t pitch, uint64_t
   static_assert(sizeof(CUtensorMap) == sizeof(fpb::TmaDesc), "tensor map size");
   cuuint64_t dims[2] = {pitch, rows};
   cuuint64_t strides[1] = {pitch};
-  cuuint32_t box[2] = {(cuuint32_t)fpb::kTmaStageCols, (cuuint32_t)fpb::kTmaRows};
+  cuuint32_t box[2] = {(cuuint32_t)fpb::kTmaStageCols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult rc = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
                        const_cast<uint8_t*>(base), dims, strides, box, estr,
@@ -416,6 +424,42 @@ int make_tensor_map(fpb_handle* h, const uint8_t* base, uint64_t pitch, uint64_t
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS)
     FPB_FAIL(h, std::string("cuTensorMapEncodeTiled failed, code ") + std::to_string((int)rc));
+  return 0;
+}
+
+// Fused single-pass perform_op (fpb_fused.cuh): one persistent CTA per SM owns
+// <= kFSpc column stripes.  Used when every SM gets at least two stripes (below
+// that the two-kernel path fills the GPU better) and the accumulators of a CTA's
+// stripes fit in registers; FPB_FUSED=0|1 forces the choice where it is feasible.
+int setup_fused(fpb_handle* h) {
+  h->f_nstripes = (uint32_t)((h->pitch_s + 127) / 128);
+  h->f_grid = std::min<uint32_t>((uint32_t)h->sm_count, h->f_nstripes);
+  const uint32_t spc = (h->f_nstripes + h->f_grid - 1) / h->f_grid;
+  const bool feasible = spc <= (uint32_t)fpb::kFSpc;
+  bool want = feasible && h->f_nstripes >= 2u * (uint32_t)h->sm_count;
+  if (const char* fv = getenv("FPB_FUSED")) want = feasible && atoi(fv) != 0;
+  if (want) {
+    int coop = 0;
+    FPB_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    if (!coop) want = false;
+  }
+  h->use_fused = want;
+  if (!want) return 0;
+  h->f_nslabs = (uint32_t)((h->nsnps + fpb::kFRows - 1) / fpb::kFRows);
+  h->f_gpad = (h->f_grid + 31) / 32 * 32;
+  if (const char* wv = getenv("FPB_FUSED_WINDOW"))
+    h->f_window = (uint32_t)std::min(std::max(atoi(wv), 1), fpb::kFASlots);
+  if (const char* pv = getenv("FPB_FUSED_POL1")) h->f_pol1 = (uint32_t)atoi(pv);
+  if (const char* pv = getenv("FPB_FUSED_POL2")) h->f_pol2 = (uint32_t)atoi(pv);
+  if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_f, fpb::kFRows)) return 1;
+  FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_fused_op, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fpb::kFSmemBytes));
+  FPB_CUDA(h, cudaMalloc(&h->d_fpart,
+                         sizeof(double) * (size_t)fpb::kFASlots * fpb::kFRows * h->f_gpad));
+  FPB_CUDA(h, cudaMalloc(&h->d_ybuf, sizeof(double) * h->n));
+  FPB_CUDA(h, cudaMalloc(&h->d_fsync, sizeof(uint32_t) * (2 * (size_t)h->f_nslabs + 1)));
+  FPB_CUDA(h, cudaMemsetAsync(h->d_fsync, 0, sizeof(uint32_t) * (2 * (size_t)h->f_nslabs + 1),
+                              h->stream));
   return 0;
 }
 
@@ -549,6 +593,7 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        fpb::kTmaSmemBytes));
     }
+    if (h->single_copy && setup_fused(h)) return 1;
   }
   uint64_t max_chunks = std::max(h->nchunks_s, h->nchunks_i);
   // the K-major slices of the single-copy second half need 8 bytes per SNP, padded to whole tiles
@@ -757,6 +802,78 @@ void imma_prod_tail(fpb_handle* h, double* d_y) {
   h->launches++;
 }
 
+// y = X X' x in one pass over the packed matrix (fpb_fused.cuh).  The missing-genotype
+// sums of the first half only depend on x and run before the fused kernel; the
+// second gather needs every corr_j and runs after it.
+void fused_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
+  if (h->nmissing) {
+    fork_mark(h);
+    gather_launch(h, true, d_x);
+  }
+  vec_partials(h, d_x, h->n);
+  const uint32_t nwq = h->nchunks_s * fpb::kChunkWords;
+  fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(
+      d_x, h->n, nwq, h->d_pmax, h->d_psum, h->nparts, h->d_sc + 0, h->d_slices);
+  cudaMemsetAsync(h->d_fsync, 0, sizeof(uint32_t) * 2 * (size_t)h->f_nslabs, h->stream);
+  if (h->nmissing) join_gather(h);
+  fpb::FusedArgs a;
+  a.n = (uint32_t)h->n;
+  a.nsnps = (uint32_t)h->nsnps;
+  a.nslabs = h->f_nslabs;
+  a.nstripes = h->f_nstripes;
+  a.window = h->f_window;
+  a.gpad = h->f_gpad;
+  a.mx_tiles = h->nmissing ? h->gtiles_s : 0;
+  a.pol1 = h->f_pol1;
+  a.pol2 = h->f_pol2;
+  a.xslices = h->d_slices;
+  a.sc_x = h->d_sc + 0;
+  a.scale = h->d_scale;
+  a.mxv = h->nmissing ? h->d_mx : nullptr;
+  a.part = h->d_fpart;
+  a.cnt = h->d_fsync;
+  a.cnt2 = h->d_fsync + h->f_nslabs;
+  a.a_out = h->d_a;
+  a.corr_out = h->d_corr;
+  a.ybuf = h->d_ybuf;
+  a.f_out = h->d_part;
+  a.err = h->d_fsync + 2 * (size_t)h->f_nslabs;
+  void* params[] = {(void*)&h->tm_f, (void*)&a};
+  if (h->time_gemv) cudaEventRecord(h->kev[0], h->stream);
+  cudaLaunchCooperativeKernel((const void*)fpb::k_fused_op, dim3(h->f_grid), dim3(fpb::kFThreads),
+                              params, (size_t)fpb::kFSmemBytes, h->stream);
+  if (h->time_gemv) cudaEventRecord(h->kev[1], h->stream);
+  h->fused_used = true;
+  if (h->nmissing) {
+    fork_mark(h);
+    gather_launch(h, false, h->d_corr);
+  }
+  fpb::k_fused_sum_b<<<1, 1024, 0, h->stream>>>(h->d_a, h->d_scale, (uint32_t)h->nsnps,
+                                                 h->d_sc + 1);
+  if (h->nmissing) join_gather(h);
+  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
+  fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, 1, h->part_stride, h->n, h->d_sc + 1,
+                                                  h->nmissing ? h->d_mc : nullptr, h->gtiles_i,
+                                                  d_y);
+  h->launches += 4;  // slicing, fused op, Sb, finalize (gathers and partials count themselves)
+}
+
+// The fused kernel reports a timed-out wait (a protocol failure) through a device
+// word instead of hanging; surfaced at the API's synchronisation points.
+int check_fused(fpb_handle* h) {
+  if (!h->fused_used) return 0;
+  h->fused_used = false;
+  uint32_t code = 0;
+  uint32_t* d_err = h->d_fsync + 2 * (size_t)h->f_nslabs;
+  FPB_CUDA(h, cudaMemcpyAsync(&code, d_err, sizeof(code), cudaMemcpyDeviceToHost, h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (code) {
+    cudaMemsetAsync(d_err, 0, sizeof(code), h->stream);
+    FPB_FAIL(h, "fused perform_op kernel: wait timed out (code " + std::to_string(code) + ")");
+  }
+  return 0;
+}
+
 // in-memory matrix path (svdwide.cpp:4-12)
 void dense_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
   fpb::k_dense_gemv_t<<<(uint32_t)h->nsnps, 256, 0, h->stream>>>(h->d_X, h->n, d_x, d_t);
@@ -799,6 +916,8 @@ void launch_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
   if (h->dense) {  // y = mat * (mat' x), svdwide.cpp:10
     dense_crossprod(h, d_x, h->d_t);
     dense_prod(h, h->d_t, d_y);
+  } else if (h->use_imma && h->use_fused) {
+    fused_perform_op(h, d_x, d_y);
   } else if (h->use_imma) {
     imma_crossprod(h, d_x, nullptr, true);
     imma_prod_tail(h, d_y);
@@ -1044,6 +1163,9 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_sc);
   cudaFree(h->d_mx);
   cudaFree(h->d_mc);
+  cudaFree(h->d_fpart);
+  cudaFree(h->d_ybuf);
+  cudaFree(h->d_fsync);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->side) cudaStreamDestroy(h->side);
@@ -1099,7 +1221,7 @@ int fpb_sync(fpb_handle* h) {
   if (!h) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
   FPB_CUDA(h, cudaGetLastError());
-  return 0;
+  return check_fused(h);
 }
 
 // ------------------------------ device-pointer ops -------------------------
@@ -1148,7 +1270,7 @@ static int host_op(fpb_handle* h, const double* in, uint32_t k, double* out, uin
   FPB_CUDA(h, cudaMemcpyAsync(out, h->d_out, sizeof(double) * out_rows * k,
                               cudaMemcpyDeviceToHost, h->stream));
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  return 0;
+  return check_fused(h);
 }
 
 int fpb_perform_op_multi(fpb_handle* h, const double* m_in, uint32_t k, double* y_out) {
@@ -1240,8 +1362,6 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
   const auto t0 = now();
   if (h->solver && !h->solver->matches(h->n, nev, ncv)) {
     delete h->solver;
-  for (int i = 0; i < 4; i++)
-    if (h->kev[i]) cudaEventDestroy(h->kev[i]);
     h->solver = nullptr;
   }
   if (!h->solver) h->solver = new fpb::Irlm(h->n, nev, ncv, h->stream, op);
@@ -1258,7 +1378,7 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
     cudaEventDestroy(evs[i]);
     cudaEventDestroy(evs[i + 1]);
   }
-  if (op_rc) {
+  if (op_rc || check_fused(h)) {
     solver.set_op(nullptr);
     return 1;
   }
@@ -1321,25 +1441,44 @@ int fpb_time_perform_op(fpb_handle* h, const double* d_x, double* d_y, uint32_t 
     for (int i = 0; i < 4; i++)
       if (!h->kev[i]) cudaEventCreate(&h->kev[i]);
     h->time_gemv = h->use_imma;
+    const bool fused = h->use_imma && h->use_fused && !h->dense;
     cudaEventRecord(e0, h->stream);
-    launch_crossprod(h, d_x, h->d_t);
-    cudaEventRecord(e1, h->stream);
-    cudaEventRecord(e2, h->stream);
-    launch_prod(h, h->d_t, d_y);
+    if (fused) {
+      // one launch does both halves: [0] = the whole op, [2] = the fused kernel alone
+      launch_perform_op(h, d_x, d_y);
+      cudaEventRecord(e1, h->stream);
+      cudaEventRecord(e2, h->stream);
+    } else {
+      launch_crossprod(h, d_x, h->d_t);
+      cudaEventRecord(e1, h->stream);
+      cudaEventRecord(e2, h->stream);
+      launch_prod(h, h->d_t, d_y);
+    }
     cudaEventRecord(e3, h->stream);
     h->time_gemv = false;
     FPB_CUDA(h, cudaEventSynchronize(e3));
     cudaEventElapsedTime(&ms_kernels_out[0], e0, e1);
     cudaEventElapsedTime(&ms_kernels_out[1], e2, e3);
     ms_kernels_out[2] = ms_kernels_out[3] = 0.f;
-    if (h->use_imma) {
+    if (fused) {
+      ms_kernels_out[1] = 0.f;
+      cudaEventElapsedTime(&ms_kernels_out[2], h->kev[0], h->kev[1]);
+    } else if (h->use_imma) {
       cudaEventElapsedTime(&ms_kernels_out[2], h->kev[0], h->kev[1]);
       cudaEventElapsedTime(&ms_kernels_out[3], h->kev[2], h->kev[3]);
     }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   FPB_CUDA(h, cudaGetLastError());
-  return 0;
+  return check_fused(h);
+}
+
+unsigned fpb_path_info(const fpb_handle* h) {
+  if (!h) return 0;
+  return (h->dense ? FPB_PATH_DENSE : 0u) | (h->use_imma ? FPB_PATH_TENSOR : 0u) |
+         (h->use_imma && h->use_tma ? FPB_PATH_TMA : 0u) |
+         (h->use_imma && h->single_copy ? FPB_PATH_SINGLE_COPY : 0u) |
+         (h->use_imma && h->use_fused ? FPB_PATH_FUSED : 0u);
 }
 
 }  // extern "C"

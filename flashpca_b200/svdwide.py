@@ -124,6 +124,10 @@ class SVDWideOnline:
         check(self.lib.fpb_get_meansd(self.h, out.ctypes.data), self.h)
         return out
 
+    def path_info(self) -> int:
+        """Compute path chosen at staging: bit mask of _lib.PATH_*."""
+        return int(self.lib.fpb_path_info(self.h))
+
     def bed_payload(self) -> np.ndarray:
         out = np.zeros(((self.n + 3) // 4) * self.p, dtype=np.uint8)
         check(self.lib.fpb_get_bed(self.h, out.ctypes.data), self.h)

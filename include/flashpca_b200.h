@@ -166,9 +166,19 @@ void fpb_pca_phase_times(const fpb_handle *h, double out_seconds[4]);
  * NULL, else 4 floats) receives, from one further op: [0] the X'x half, [1] the
  * X t half (each with its small kernels), [2], [3] the contraction kernel of
  * each half alone (events recorded immediately around its launch; 0 on the
- * generic FP64 path). */
+ * generic FP64 path).  When the fused single-pass kernel is in use
+ * (fpb_path_info & FPB_PATH_FUSED): [0] the whole op, [2] the fused kernel
+ * alone, [1] = [3] = 0. */
 int fpb_time_perform_op(fpb_handle *h, const double *d_x, double *d_y, uint32_t reps,
                         float *ms_per_op_out, float *ms_kernels_out);
+
+/* Which compute path the handle selected at staging (bit mask). */
+#define FPB_PATH_DENSE 1u       /* in-memory matrix (fpb_create_dense) */
+#define FPB_PATH_TENSOR 2u      /* exact int8-sliced tensor-core contraction */
+#define FPB_PATH_TMA 4u         /* TMA + mbarrier pipelines */
+#define FPB_PATH_SINGLE_COPY 8u /* both halves read the one SNP-major copy */
+#define FPB_PATH_FUSED 16u      /* perform_op reads HBM once (fused two-phase kernel) */
+unsigned fpb_path_info(const fpb_handle *h);
 /* Number of kernels this library has launched on the handle so far. */
 uint64_t fpb_launch_count(const fpb_handle *h);
 

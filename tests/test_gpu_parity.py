@@ -465,3 +465,129 @@ def test_pca_ndim50_like_the_r_tests(native_lib):
     for j in range(50):
         c = abs(np.corrcoef(r.Px[:, j], ref["Px"][:, j])[0, 1])
         assert c > 1 - 1e-6, (j, c)
+
+
+# ---------------------------------------------------------------------------
+# Fused single-pass perform_op (fpb_fused.cuh).  FPB_FUSED=1 forces it at sizes
+# the oracle can check (by default it is used from ~150k individuals up).
+# ---------------------------------------------------------------------------
+@pytest.fixture
+def fused(monkeypatch):
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    monkeypatch.delenv("FPB_GEMV", raising=False)
+    monkeypatch.setenv("FPB_FUSED", "1")
+
+
+def _is_fused(op):
+    from flashpca_b200 import _lib
+    return bool(op.path_info() & _lib.PATH_FUSED)
+
+
+@pytest.mark.parametrize("name", ["data_chr1", "hapmap3"])
+def test_fused_op_fixtures(native_lib, fused, monkeypatch, name):
+    _, payload, n, p = load_fixture(name)
+    op = _mk(payload, n, p)
+    assert _is_fused(op)
+    orc = O.COracle(payload, n, p)
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal(n)
+    y_ref = orc.perform_op(x, 0)
+    y = op.perform_op(x)
+    assert _relerr(y, y_ref) <= OP_RTOL
+    assert np.array_equal(op.perform_op(x), y)               # bit-reproducible
+    m = rng.standard_normal((n, 3))
+    assert _relerr(op.perform_op_mat(m), orc.perform_op(m, 0)) <= OP_RTOL
+    # the one-sided ops of a fused handle still take the two-kernel path
+    assert _relerr(op.crossprod(x), orc.crossprod(x)) <= OP_RTOL
+    # same result as the two-kernel path up to the FP64 recombination order
+    monkeypatch.setenv("FPB_FUSED", "0")
+    two = _mk(payload, n, p)
+    assert not _is_fused(two)
+    assert _relerr(y, two.perform_op(x)) <= 1e-13
+    # scale invariance, zero, unit and non-finite vectors
+    for sc in (1e-300, 1e-30, 1e30, 1e250):
+        assert _relerr(op.perform_op(x * sc) / sc, y) <= OP_RTOL
+    assert np.all(op.perform_op(np.zeros(n)) == 0.0)
+    e = np.zeros(n)
+    e[17] = 1.0
+    assert _relerr(op.perform_op(e), orc.perform_op(e, 0)) <= OP_RTOL
+    assert np.isnan(op.perform_op(np.full(n, np.nan))).all()
+    assert _relerr(op.perform_op(x), y_ref) <= OP_RTOL       # state is clean after a NaN op
+
+
+@pytest.mark.parametrize("n,p", [(1, 3), (3, 1), (4, 5), (63, 9), (64, 64), (65, 130), (513, 129),
+                                 (1000, 17), (4099, 257), (16384 + 5, 40), (3000, 1100)])
+def test_fused_op_ragged_shapes(native_lib, fused, n, p):
+    rng = np.random.default_rng(n * 1000 + p + 1)
+    codes = rng.choice(np.array([0, 1, 2, 3], dtype=np.uint8), size=(n, p),
+                       p=[0.15, 0.02, 0.38, 0.45])
+    payload = _pack(codes)
+    op = _mk(payload, n, p)
+    assert _is_fused(op)
+    orc = O.COracle(payload, n, p)
+    x = rng.standard_normal(n)
+    y_ref = orc.perform_op(x, 0)
+    y = op.perform_op(x)
+    assert np.isfinite(y).all()
+    assert np.abs(y - y_ref).max() <= OP_RTOL * max(np.abs(y_ref).max(), 1.0)
+    assert np.array_equal(op.perform_op(x), y)
+    op.close()
+
+
+def test_fused_op_exponent_growth_and_dead_snps(native_lib, fused):
+    """The running exponent of a grows along the SNP axis (rare variants late in
+    the file have small sd, hence large a_j): the second half must drain its
+    accumulators and carry on; monomorphic and all-missing SNPs contribute 0."""
+    n, p = 2100, 1500
+    rng = np.random.default_rng(77)
+    maf = np.concatenate([rng.uniform(0.3, 0.5, 600), rng.uniform(0.002, 0.01, 400),
+                          np.zeros(100), rng.uniform(0.0005, 0.002, 400)])
+    g = rng.binomial(2, maf[None, :], size=(n, p))
+    codes = np.where(g == 2, 0, np.where(g == 1, 2, 3)).astype(np.uint8)
+    codes[rng.random((n, p)) < 0.002] = 1
+    codes[:, 1050] = 1                                      # all missing
+    payload = _pack(codes)
+    op = _mk(payload, n, p)
+    assert _is_fused(op)
+    orc = O.COracle(payload, n, p)
+    x = rng.standard_normal(n)
+    y_ref = orc.perform_op(x, 0)
+    y = op.perform_op(x)
+    assert np.abs(y - y_ref).max() <= OP_RTOL * np.abs(y_ref).max()
+    assert np.array_equal(op.perform_op(x), y)
+
+
+def test_fused_solver_matches_two_kernel_solver(native_lib, fused, monkeypatch):
+    _, payload, n, p = load_fixture("hapmap3")
+    op = _mk(payload, n, p)
+    assert _is_fused(op)
+    got = op.pca(10, 21, 500, 1e-6)
+    monkeypatch.setenv("FPB_FUSED", "0")
+    two = _mk(payload, n, p).pca(10, 21, 500, 1e-6)
+    assert got["nconv"] == 10
+    assert np.abs(got["values"] / two["values"] - 1).max() < 1e-9
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, 10)
+    assert np.abs(got["values"] / p / ref["d"] - 1).max() < 1e-6
+
+
+def test_fused_is_default_at_full_size(native_lib, monkeypatch):
+    """BASELINE config 2 (500,000 x 100,000): the fused kernel is the default
+    path; checked against the two-kernel path on the same HBM-resident matrix
+    and for bit-reproducibility."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs > 60 GB HBM")
+    from flashpca_b200.synth import SynthSpec
+    monkeypatch.delenv("FPB_FUSED", raising=False)
+    s = SynthSpec(500000, 20000, seed=20240603)
+    op = s.create_operator()
+    assert _is_fused(op)
+    x = np.random.default_rng(2).standard_normal(s.n)
+    y = op.perform_op(x)
+    assert np.array_equal(op.perform_op(x), y)
+    op.close()
+    monkeypatch.setenv("FPB_FUSED", "0")
+    two = s.create_operator()
+    assert not _is_fused(two)
+    assert _relerr(y, two.perform_op(x)) <= 1e-13
