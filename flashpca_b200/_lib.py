@@ -53,6 +53,7 @@ SIGNATURES = {
     "fpb_time_perform_op": (_i, [_vp, _vp, _vp, _u32, _c.POINTER(_c.c_float), _vp]),
     "fpb_launch_count": (_u64, [_vp]),
     "fpb_path_info": (_c.c_uint, [_vp]),
+    "fpb_fused_debug": (_i, [_vp, _vp, _u64]),
 }
 
 # fpb_path_info bits (include/flashpca_b200.h)

@@ -135,9 +135,11 @@ struct fpb_handle {
   // fused single-pass perform_op (fpb_fused.cuh)
   bool use_fused = false;
   fpb::TmaDesc tm_f;                       // box 128 B x kFRows rows over gs
-  uint32_t f_grid = 0, f_nslabs = 0, f_nstripes = 0, f_gpad = 0, f_window = 3, f_pol1 = 0, f_pol2 = 1;
-  double *d_fpart = nullptr, *d_ybuf = nullptr;
-  uint32_t* d_fsync = nullptr;             // cnt[nslabs], cnt2[nslabs], err
+  uint32_t f_grid = 0, f_nslabs = 0, f_nstripes = 0, f_gpad = 0, f_window = 4, f_pol1 = 0, f_pol2 = 1, f_prefetch = 1;
+  double *d_fpart = nullptr, *d_ybuf = nullptr, *d_arep = nullptr;
+  uint64_t f_rep_stride = 0;
+  uint32_t* d_fsync = nullptr;             // watchdog error word
+  unsigned long long* d_fdbg = nullptr;    // FPB_FUSED_DEBUG: time stamps of two CTAs
   bool fused_used = false;                 // an op ran through the fused kernel since the last check
   // host-pointer API staging (grown on demand)
   double* d_in = nullptr;
@@ -428,15 +430,16 @@ int make_tensor_map(fpb_handle* h, const uint8_t* base, uint64_t pitch, uint64_t
 }
 
 // Fused single-pass perform_op (fpb_fused.cuh): one persistent CTA per SM owns
-// <= kFSpc column stripes.  Used when every SM gets at least two stripes (below
-// that the two-kernel path fills the GPU better) and the accumulators of a CTA's
-// stripes fit in registers; FPB_FUSED=0|1 forces the choice where it is feasible.
+// <= kFSpc column stripes.  Opt-in (FPB_FUSED=1): it reads HBM once per op (ncu:
+// 13.2 GB vs 25.1 GB) but on B200 the two halves do not overlap on an SM -- the
+// kernel is bound by instruction issue (mma.sync + LOP3 decode), 4.2 ms against
+// 3.7 ms for the two HBM-bound kernels (profiles/r01_fused_*).
 int setup_fused(fpb_handle* h) {
   h->f_nstripes = (uint32_t)((h->pitch_s + 127) / 128);
   h->f_grid = std::min<uint32_t>((uint32_t)h->sm_count, h->f_nstripes);
   const uint32_t spc = (h->f_nstripes + h->f_grid - 1) / h->f_grid;
   const bool feasible = spc <= (uint32_t)fpb::kFSpc;
-  bool want = feasible && h->f_nstripes >= 2u * (uint32_t)h->sm_count;
+  bool want = false;
   if (const char* fv = getenv("FPB_FUSED")) want = feasible && atoi(fv) != 0;
   if (want) {
     int coop = 0;
@@ -446,20 +449,28 @@ int setup_fused(fpb_handle* h) {
   h->use_fused = want;
   if (!want) return 0;
   h->f_nslabs = (uint32_t)((h->nsnps + fpb::kFRows - 1) / fpb::kFRows);
-  h->f_gpad = (h->f_grid + 31) / 32 * 32;
+  h->f_gpad = (fpb::kFP1Groups * h->f_grid + 31) / 32 * 32;
   if (const char* wv = getenv("FPB_FUSED_WINDOW"))
-    h->f_window = (uint32_t)std::min(std::max(atoi(wv), 1), fpb::kFASlots);
+    h->f_window = (uint32_t)std::min(std::max(atoi(wv), 2), fpb::kFASlots);  // >= 2: lagged slot release
   if (const char* pv = getenv("FPB_FUSED_POL1")) h->f_pol1 = (uint32_t)atoi(pv);
   if (const char* pv = getenv("FPB_FUSED_POL2")) h->f_pol2 = (uint32_t)atoi(pv);
+  if (const char* pv = getenv("FPB_FUSED_PREFETCH")) h->f_prefetch = (uint32_t)std::max(0, atoi(pv));
   if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_f, fpb::kFRows)) return 1;
   FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_fused_op, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpb::kFSmemBytes));
-  FPB_CUDA(h, cudaMalloc(&h->d_fpart,
-                         sizeof(double) * (size_t)fpb::kFASlots * fpb::kFRows * h->f_gpad));
+  const size_t part_bytes = sizeof(double) * (size_t)fpb::kFASlots * fpb::kFRows * h->f_gpad;
+  FPB_CUDA(h, cudaMalloc(&h->d_fpart, part_bytes));
+  FPB_CUDA(h, cudaMemsetAsync(h->d_fpart, 0xFF, part_bytes, h->stream));  // all-ones = free
   FPB_CUDA(h, cudaMalloc(&h->d_ybuf, sizeof(double) * h->n));
-  FPB_CUDA(h, cudaMalloc(&h->d_fsync, sizeof(uint32_t) * (2 * (size_t)h->f_nslabs + 1)));
-  FPB_CUDA(h, cudaMemsetAsync(h->d_fsync, 0, sizeof(uint32_t) * (2 * (size_t)h->f_nslabs + 1),
-                              h->stream));
+  h->f_rep_stride = (uint64_t)h->f_nslabs * fpb::kFRows;
+  FPB_CUDA(h, cudaMalloc(&h->d_arep, sizeof(double) * fpb::kFReplicas * h->f_rep_stride));
+  FPB_CUDA(h, cudaMalloc(&h->d_fsync, sizeof(uint32_t)));
+  FPB_CUDA(h, cudaMemsetAsync(h->d_fsync, 0, sizeof(uint32_t), h->stream));
+  if (getenv("FPB_FUSED_DEBUG")) {
+    const size_t db = sizeof(unsigned long long) * 2 * fpb::kFDbgSlabs * fpb::kFDbgEvents;
+    FPB_CUDA(h, cudaMalloc(&h->d_fdbg, db));
+    FPB_CUDA(h, cudaMemsetAsync(h->d_fdbg, 0, db, h->stream));
+  }
   return 0;
 }
 
@@ -814,7 +825,8 @@ void fused_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
   const uint32_t nwq = h->nchunks_s * fpb::kChunkWords;
   fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(
       d_x, h->n, nwq, h->d_pmax, h->d_psum, h->nparts, h->d_sc + 0, h->d_slices);
-  cudaMemsetAsync(h->d_fsync, 0, sizeof(uint32_t) * 2 * (size_t)h->f_nslabs, h->stream);
+  cudaMemsetAsync(h->d_arep, 0xFF, sizeof(double) * fpb::kFReplicas * h->f_rep_stride,
+                  h->stream);  // all-ones = not written
   if (h->nmissing) join_gather(h);
   fpb::FusedArgs a;
   a.n = (uint32_t)h->n;
@@ -826,18 +838,24 @@ void fused_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
   a.mx_tiles = h->nmissing ? h->gtiles_s : 0;
   a.pol1 = h->f_pol1;
   a.pol2 = h->f_pol2;
+  a.prefetch = h->f_prefetch;
+  {
+    static const char* dm = getenv("FPB_FUSED_DBGMODE");
+    a.dbg_mode = dm ? (uint32_t)atoi(dm) : 0u;
+  }
   a.xslices = h->d_slices;
   a.sc_x = h->d_sc + 0;
   a.scale = h->d_scale;
   a.mxv = h->nmissing ? h->d_mx : nullptr;
   a.part = h->d_fpart;
-  a.cnt = h->d_fsync;
-  a.cnt2 = h->d_fsync + h->f_nslabs;
   a.a_out = h->d_a;
+  a.a_rep = h->d_arep;
+  a.rep_stride = h->f_rep_stride;
   a.corr_out = h->d_corr;
   a.ybuf = h->d_ybuf;
   a.f_out = h->d_part;
-  a.err = h->d_fsync + 2 * (size_t)h->f_nslabs;
+  a.err = h->d_fsync;
+  a.dbg = h->d_fdbg;
   void* params[] = {(void*)&h->tm_f, (void*)&a};
   if (h->time_gemv) cudaEventRecord(h->kev[0], h->stream);
   cudaLaunchCooperativeKernel((const void*)fpb::k_fused_op, dim3(h->f_grid), dim3(fpb::kFThreads),
@@ -864,11 +882,13 @@ int check_fused(fpb_handle* h) {
   if (!h->fused_used) return 0;
   h->fused_used = false;
   uint32_t code = 0;
-  uint32_t* d_err = h->d_fsync + 2 * (size_t)h->f_nslabs;
+  uint32_t* d_err = h->d_fsync;
   FPB_CUDA(h, cudaMemcpyAsync(&code, d_err, sizeof(code), cudaMemcpyDeviceToHost, h->stream));
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (code) {
     cudaMemsetAsync(d_err, 0, sizeof(code), h->stream);
+    cudaMemsetAsync(h->d_fpart, 0xFF,
+                    sizeof(double) * (size_t)fpb::kFASlots * fpb::kFRows * h->f_gpad, h->stream);
     FPB_FAIL(h, "fused perform_op kernel: wait timed out (code " + std::to_string(code) + ")");
   }
   return 0;
@@ -1165,7 +1185,9 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_mc);
   cudaFree(h->d_fpart);
   cudaFree(h->d_ybuf);
+  cudaFree(h->d_arep);
   cudaFree(h->d_fsync);
+  cudaFree(h->d_fdbg);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->side) cudaStreamDestroy(h->side);
@@ -1471,6 +1493,15 @@ int fpb_time_perform_op(fpb_handle* h, const double* d_x, double* d_y, uint32_t 
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   FPB_CUDA(h, cudaGetLastError());
   return check_fused(h);
+}
+
+int fpb_fused_debug(fpb_handle* h, unsigned long long* out, uint64_t count) {
+  if (!h || !out) FPB_FAIL(h, "null argument");
+  const uint64_t have = 2ull * fpb::kFDbgSlabs * fpb::kFDbgEvents;
+  if (!h->d_fdbg || count < have) FPB_FAIL(h, "no fused debug stamps (set FPB_FUSED_DEBUG=1)");
+  FPB_CUDA(h, cudaMemcpy(out, h->d_fdbg, sizeof(unsigned long long) * have,
+                         cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 unsigned fpb_path_info(const fpb_handle* h) {

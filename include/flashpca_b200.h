@@ -179,6 +179,11 @@ int fpb_time_perform_op(fpb_handle *h, const double *d_x, double *d_y, uint32_t 
 #define FPB_PATH_SINGLE_COPY 8u /* both halves read the one SNP-major copy */
 #define FPB_PATH_FUSED 16u      /* perform_op reads HBM once (fused two-phase kernel) */
 unsigned fpb_path_info(const fpb_handle *h);
+
+/* Debug: with FPB_FUSED_DEBUG=1 in the environment at staging, the fused kernel
+ * records globaltimer stamps of its cross-CTA protocol for the first 256 slabs
+ * of CTA 0 and of the last CTA: out[2][256][8] (count >= 4096). */
+int fpb_fused_debug(fpb_handle *h, unsigned long long *out, uint64_t count);
 /* Number of kernels this library has launched on the handle so far. */
 uint64_t fpb_launch_count(const fpb_handle *h);
 

@@ -24,11 +24,10 @@ ms = ctypes.c_float()
 kms = (ctypes.c_float * 4)()
 ref = None
 configs = [dict(FPB_FUSED="0")]
-for w, p1, p2 in itertools.product((1, 2, 3, 4), (0, 2), (1, 0)):
-    configs.append(dict(FPB_FUSED="1", FPB_FUSED_WINDOW=str(w), FPB_FUSED_POL1=str(p1),
-                        FPB_FUSED_POL2=str(p2)))
+for w, pf in itertools.product((3, 4, 5, 6, 8), (0, 1)):
+    configs.append(dict(FPB_FUSED="1", FPB_FUSED_WINDOW=str(w), FPB_FUSED_PREFETCH=str(pf)))
 for cfg in configs:
-    for k in ("FPB_FUSED", "FPB_FUSED_WINDOW", "FPB_FUSED_POL1", "FPB_FUSED_POL2"):
+    for k in ("FPB_FUSED", "FPB_FUSED_WINDOW", "FPB_FUSED_POL1", "FPB_FUSED_POL2", "FPB_FUSED_PREFETCH"):
         os.environ.pop(k, None)
     os.environ.update(cfg)
     op = spec.create_operator(device=0)
