@@ -625,10 +625,9 @@ k_fused_op(const __grid_constant__ TmaDesc tmap, const __grid_constant__ FusedAr
                   j == 0 ? wv[t][0].x : j == 1 ? wv[t][0].y : j == 2 ? wv[t][0].z : wv[t][0].w;
               const uint32_t xb =
                   j == 0 ? wv[t][1].x : j == 1 ? wv[t][1].y : j == 2 ? wv[t][1].z : wv[t][1].w;
-              mma_u8s8(acc[u][t][0], xa & 0x03030303u, xb & 0x03030303u, xa & 0x0C0C0C0Cu,
-                       xb & 0x0C0C0C0Cu, bv.x, bv.y);
-              mma_u8s8(acc[u][t][1], xa & 0x30303030u, xb & 0x30303030u, xa & 0xC0C0C0C0u,
-                       xb & 0xC0C0C0C0u, bv.z, bv.w);
+              mma_u8s8(acc[u][t][0], xa & 0x03030303u, xb & 0x03030303u, xa & 0x0F0F0F0Fu,
+                       xb & 0x0F0F0F0Fu, bv.x, bv.y);
+              mma_u8s8(acc[u][t][1], xa & 0x3F3F3F3Fu, xb & 0x3F3F3F3Fu, xa, xb, bv.z, bv.w);
             }
           }
         }
@@ -637,7 +636,7 @@ k_fused_op(const __grid_constant__ TmaDesc tmap, const __grid_constant__ FusedAr
       // the CTA's partial E of the slab's SNPs -> mailboxes part[s % ring][row][cta]
 #pragma unroll
       for (int t = 0; t < 2; t++) {
-        int sum4[4];  // exact: |sum| < 4 x 3584 x 192 x 64
+        int sum4[4];  // exact: |sum| <= 3584 x 255 x 127
 #pragma unroll
         for (int c = 0; c < 4; c++)
           sum4[c] = (acc[0][t][0][c] + acc[0][t][1][c]) + (acc[1][t][0][c] + acc[1][t][1][c]);

@@ -23,9 +23,11 @@
 // step delta = 2^(ex-54), ex = exponent of max|x|: Q_i = rint(x_i / (4^f delta))
 // where f = (column & 3) is the position of the genotype inside its byte, and
 // Q_i is cut into 8 balanced base-128 digits (int8).  The A operand is the packed
-// word ANDed with 0x03 / 0x0C / 0x30 / 0xC0 byte masks -- one LOP3 per 4
-// genotypes, no shifts: field f then carries e * 4^f, which the 4^-f in Q_i
-// undoes.  Products and int32 accumulation are exact; slices are recombined in
+// word ANDed with a byte mask -- at most one LOP3 per 4 genotypes, no shifts:
+// field f carries e * 4^f, which the 4^-f in Q_i undoes.  The masks are
+// cumulative (0x03, 0x0F, 0x3F, none: the fourth operand is the raw word, 3 LOP3
+// per 4 operands); the fields are separated again by storing digit DIFFERENCES
+// on the B side (first half) or by differencing the accumulators (second half).  Products and int32 accumulation are exact; slices are recombined in
 // FP64 (sum_s 128^s D_s, every term exact).  The only rounding is the input
 // quantisation, <= 2^-48 max|x| per element.
 #pragma once
@@ -40,7 +42,8 @@ namespace fpb {
 constexpr int kSliceBits = 54;   // |Q| < 2^54
 constexpr int kChunkBytes = 512; // packed bytes of one row per pipeline chunk (2048 columns)
 constexpr int kChunkWords = kChunkBytes / 4;     // 128 word-columns
-constexpr int kFlushChunks = 32;                 // int32 accumulators -> FP64 every 65536 columns
+constexpr int kFlushChunks = 24;                 // int32 accumulators -> FP64 every 49152 columns
+                                                 // (49152 x 255 x 127 < 2^31)
 
 struct VecScale {   // written by k_slice_vec, read by the finalize kernels
   double sum;       // sum of a vector (deterministic order)
@@ -187,9 +190,13 @@ k_slice_vec(const double* __restrict__ v, uint64_t n, uint32_t nwq,
   if (wq >= nwq) return;
   const int ex = sc.ex;
   const bool live = sc.delta > 0.0;  // false for zero / non-finite vectors
+  // The contraction kernels use CUMULATIVE field masks (operand f = word & (4^(f+1) - 1), the
+  // last one the raw word): sum_f A_f p_f = sum_g 4^g e_g d_g when p_f = d_f - d_{f+1} (d_4 = 0).
+  // The stored digits are those differences, |p| <= 127.
   uint32_t dig[8][4] = {};
 #pragma unroll
   for (int b = 0; b < 4; b++) {
+    int dg[4][8];
 #pragma unroll
     for (int f = 0; f < 4; f++) {
       uint64_t i = (uint64_t)wq * 16 + 4 * b + f;
@@ -199,9 +206,16 @@ k_slice_vec(const double* __restrict__ v, uint64_t n, uint32_t nwq,
       for (int s = 0; s < 8; s++) {
         long long d = (s < 7) ? (((q + 64) & 127) - 64) : q;
         q = (q - d) >> 7;
-        dig[s][f] |= ((uint32_t)(d & 0xFF)) << (8 * b);
+        dg[f][s] = (int)d;
       }
     }
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const int pd = dg[f][s] - (f < 3 ? dg[f + 1][s] : 0);
+        dig[s][f] |= ((uint32_t)(pd & 0xFF)) << (8 * b);
+      }
   }
 #pragma unroll
   for (int s = 0; s < 8; s++)
@@ -317,10 +331,9 @@ k_imma_gemv(const uint8_t* __restrict__ G, uint64_t pitch, uint32_t R,
           for (int j = 0; j < 4; j++) {
             const int wl = (hb * 4 + u) * 16 + q * 4 + j;
             const uint4 bv = sbuf[slice_slot(wl, g)];
-            mma_u8s8(acc0, xa[j] & 0x03030303u, xb[j] & 0x03030303u, xa[j] & 0x0C0C0C0Cu,
-                     xb[j] & 0x0C0C0C0Cu, bv.x, bv.y);
-            mma_u8s8(acc1, xa[j] & 0x30303030u, xb[j] & 0x30303030u, xa[j] & 0xC0C0C0C0u,
-                     xb[j] & 0xC0C0C0C0u, bv.z, bv.w);
+            mma_u8s8(acc0, xa[j] & 0x03030303u, xb[j] & 0x03030303u, xa[j] & 0x0F0F0F0Fu,
+                     xb[j] & 0x0F0F0F0Fu, bv.x, bv.y);
+            mma_u8s8(acc1, xa[j] & 0x3F3F3F3Fu, xb[j] & 0x3F3F3F3Fu, xa[j], xb[j], bv.z, bv.w);
           }
         }
       }
@@ -384,7 +397,8 @@ constexpr int kTmaSmemUsed = kTmaStages * kTmaStageBytes + 1024 + 128;
 constexpr int kTmaSmemBytes = 232448;
 static_assert(kTmaSmemUsed <= kTmaSmemBytes, "TMA ring does not fit in shared memory");
 constexpr int kTmaConsumerWarps = 8;
-constexpr int kTmaFlushStages = 96;                 // int32 -> FP64 every 49152 columns
+constexpr int kTmaFlushStages = 96;                 // int32 -> FP64 every 49152 columns / 24576 SNP rows
+                                                    // (24576 x 255 x 64 < 2^31 with the raw-word operand)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -527,10 +541,9 @@ k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* _
         for (int t = 0; t < 2; t++) {
           const uint32_t xa = j == 0 ? w[t][0].x : j == 1 ? w[t][0].y : j == 2 ? w[t][0].z : w[t][0].w;
           const uint32_t xb = j == 0 ? w[t][1].x : j == 1 ? w[t][1].y : j == 2 ? w[t][1].z : w[t][1].w;
-          mma_u8s8(acc[t][0], xa & 0x03030303u, xb & 0x03030303u, xa & 0x0C0C0C0Cu,
-                   xb & 0x0C0C0C0Cu, bv.x, bv.y);
-          mma_u8s8(acc[t][1], xa & 0x30303030u, xb & 0x30303030u, xa & 0xC0C0C0C0u,
-                   xb & 0xC0C0C0C0u, bv.z, bv.w);
+          mma_u8s8(acc[t][0], xa & 0x03030303u, xb & 0x03030303u, xa & 0x0F0F0F0Fu,
+                   xb & 0x0F0F0F0Fu, bv.x, bv.y);
+          mma_u8s8(acc[t][1], xa & 0x3F3F3F3Fu, xb & 0x3F3F3F3Fu, xa, xb, bv.z, bv.w);
         }
       }
     }
@@ -690,10 +703,12 @@ k_imma_gemv_tma_t(const __grid_constant__ TmaDesc tmap, uint32_t C /* output len
       asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
                    : "=r"(b0), "=r"(b1)
                    : "r"(sl + (uint32_t)(((ks * 8 + g) * 4 + q) * 8)));
+      // cumulative masks: accumulator f holds sum_{g <= f} 4^g e_g a (12 LOP3 per 4 IMMAs instead
+      // of 16, the last operand is the raw packed word); the epilogue takes differences
       mma_u8s8(acc[0], a0 & 0x03030303u, a1 & 0x03030303u, a2 & 0x03030303u, a3 & 0x03030303u, b0, b1);
-      mma_u8s8(acc[1], a0 & 0x0C0C0C0Cu, a1 & 0x0C0C0C0Cu, a2 & 0x0C0C0C0Cu, a3 & 0x0C0C0C0Cu, b0, b1);
-      mma_u8s8(acc[2], a0 & 0x30303030u, a1 & 0x30303030u, a2 & 0x30303030u, a3 & 0x30303030u, b0, b1);
-      mma_u8s8(acc[3], a0 & 0xC0C0C0C0u, a1 & 0xC0C0C0C0u, a2 & 0xC0C0C0C0u, a3 & 0xC0C0C0C0u, b0, b1);
+      mma_u8s8(acc[1], a0 & 0x0F0F0F0Fu, a1 & 0x0F0F0F0Fu, a2 & 0x0F0F0F0Fu, a3 & 0x0F0F0F0Fu, b0, b1);
+      mma_u8s8(acc[2], a0 & 0x3F3F3F3Fu, a1 & 0x3F3F3F3Fu, a2 & 0x3F3F3F3Fu, a3 & 0x3F3F3F3Fu, b0, b1);
+      mma_u8s8(acc[3], a0, a1, a2, a3, b0, b1);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // see k_imma_gemv_tma
     __threadfence_block();
@@ -713,9 +728,15 @@ k_imma_gemv_tma_t(const __grid_constant__ TmaDesc tmap, uint32_t C /* output len
   double* o = out + (uint64_t)blockIdx.y * out_stride;
   const uint64_t byte_a = (uint64_t)xbyte0 + warp * 16 + g;  // packed byte of MMA row g; +8 for g+8
 #pragma unroll
-  for (int f = 0; f < 4; f++) {
+  for (int f = 0; f < 4; f++)
 #pragma unroll
     for (int k = 0; k < 4; k++) dacc[f][k] += (double)acc[f][k];
+#pragma unroll
+  for (int f = 3; f > 0; f--)  // cumulative -> per field (integers below 2^53: exact)
+#pragma unroll
+    for (int k = 0; k < 4; k++) dacc[f][k] -= dacc[f - 1][k];
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
     const double sf = ldexp(1.0, -2 * f);  // the field carried e * 4^f
     double ra = (dacc[f][0] * w0 + dacc[f][1] * w1) * sf;
     double rb = (dacc[f][2] * w0 + dacc[f][3] * w1) * sf;
