@@ -132,6 +132,10 @@ struct fpb_handle {
   bool single_copy = false;
   uint32_t ttiles = 0, ttsplits = 1, ttps = 1;
   uint64_t part_stride = 0;
+  // persistent forms of the two TMA kernels: used per half when the one-item-per-CTA grid would have
+  // fewer than ~10 waves (pipeline fill and the partial last wave then dominate); FPB_PERSIST=0|1 forces
+  bool persist_s = false, persist_t = false;
+  uint32_t psplits_s = 1, psps_s = 1, psplits_t = 1, ptps_t = 1;
   // fused single-pass perform_op (fpb_fused.cuh)
   bool use_fused = false;
   fpb::TmaDesc tm_f;                       // box 128 B x kFRows rows over gs
@@ -382,6 +386,30 @@ void pick_splits_waves(uint32_t units, uint32_t nstages, int sm_count, uint32_t*
   *splits = (nstages + *per_split - 1) / *per_split;
 }
 
+// Splits of the reduction axis for the persistent kernels: `units` output tiles x s splits
+// are dealt round-robin to one CTA per SM; pick the s that minimises
+// (most items any CTA gets) x (stages per item + epilogue).
+void pick_splits_persist(uint32_t units, uint32_t nstages, int sm_count, uint32_t* splits,
+                         uint32_t* per_split) {
+  const uint32_t G = (uint32_t)sm_count;
+  const uint32_t smax = std::max<uint32_t>(1, std::min<uint32_t>(64, nstages / 12));
+  uint32_t best = 1;
+  double best_cost = 1e300;
+  for (uint32_t sp = 1; sp <= smax; sp++) {
+    const uint32_t per = (nstages + sp - 1) / sp;
+    const uint32_t real = (nstages + per - 1) / per;
+    const uint64_t items = (uint64_t)units * real;
+    const double rounds = std::ceil((double)items / G);
+    const double cost = rounds * (per + 1.5);
+    if (cost < best_cost * 0.9999) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  *per_split = (nstages + best - 1) / best;
+  *splits = (nstages + *per_split - 1) / *per_split;
+}
+
 // debug: FPB_DEBUG_SPLITS1 / FPB_DEBUG_SPLITS2 override the split count of the first /
 // second contraction kernel (tuning sweeps)
 void override_splits(const char* env, uint32_t nstages, uint32_t* splits, uint32_t* per_split) {
@@ -594,6 +622,24 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
       h->ttsplits = (h->ttiles + h->ttps - 1) / h->ttps;
       override_splits("FPB_DEBUG_SPLITS2", h->ttiles, &h->ttsplits, &h->ttps);
     }
+    {
+      // Measured (profiles/r01_persist_sweep.txt): at 10k x 100k the persistent kernels are 9 % faster
+      // (0.141 -> 0.129 ms per op); at 500k x 100k the first half is unchanged (1.75 ms) and the
+      // second half is slower in lockstep (2.6 vs 1.88 ms), so large grids stay one-shot.
+      const char* pv = getenv("FPB_PERSIST");
+      const uint32_t ntile_s = (uint32_t)((h->nsnps + fpb::kTmaRows - 1) / fpb::kTmaRows);
+      const uint32_t few = 10u * (uint32_t)h->sm_count;
+      h->persist_s = h->single_copy && (pv ? atoi(pv) != 0 : ntile_s * h->tsplits_s < few);
+      h->persist_t = h->single_copy && (pv ? atoi(pv) != 0 : h->nstages_s * h->ttsplits < few);
+      if (h->persist_s) {
+        pick_splits_persist(ntile_s, h->nstages_s, h->sm_count, &h->psplits_s, &h->psps_s);
+        override_splits("FPB_DEBUG_SPLITS1", h->nstages_s, &h->psplits_s, &h->psps_s);
+      }
+      if (h->persist_t) {
+        pick_splits_persist(h->nstages_s, h->ttiles, h->sm_count, &h->psplits_t, &h->ptps_t);
+        override_splits("FPB_DEBUG_SPLITS2", h->ttiles, &h->psplits_t, &h->ptps_t);
+      }
+    }
     if (h->use_tma) {
       if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_s)) return 1;
       if (!h->single_copy && make_tensor_map(h, h->d_gi, h->pitch_i, h->n, &h->tm_i)) return 1;
@@ -601,6 +647,12 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        fpb::kTmaSmemBytes));
       FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fpb::kTmaSmemBytes));
+      FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma_p,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fpb::kTmaSmemBytes));
+      FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma_t_p,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        fpb::kTmaSmemBytes));
     }
@@ -613,9 +665,10 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
   FPB_CUDA(h, cudaMalloc(&h->d_slices, slice_bytes));
   FPB_CUDA(h, cudaMalloc(&h->d_part,
                          sizeof(double) * h->part_stride *
-                             std::max(std::max(std::max(h->splits_s, h->splits_i),
-                                               std::max(h->tsplits_s, h->tsplits_i)),
-                                      h->ttsplits)));
+                             std::max(std::max(std::max(std::max(h->splits_s, h->splits_i),
+                                                        std::max(h->tsplits_s, h->tsplits_i)),
+                                               h->ttsplits),
+                                      std::max(h->psplits_s, h->psplits_t))));
   FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * h->nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * h->nsnps));
   const size_t max_parts = std::max<size_t>(kVecBlocks, (h->nsnps + 255) / 256);
@@ -705,14 +758,24 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
         d_v, vlen, ngroups4, h->d_pmax, h->d_psum, h->nparts, h->d_sc + slot,
         reinterpret_cast<uint32_t*>(h->d_slices));
     if (h->time_gemv) cudaEventRecord(h->kev[2], h->stream);
-    dim3 grid(h->nstages_s, h->ttsplits);
-    fpb::k_imma_gemv_tma_t<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
-                             h->stream>>>(h->tm_s, (uint32_t)h->n,
-                                          reinterpret_cast<const uint32_t*>(h->d_slices),
-                                          h->ttiles, h->ttps, h->d_part, h->part_stride);
+    uint32_t used = h->ttsplits;
+    if (h->persist_t) {
+      const uint32_t nitems = h->nstages_s * h->psplits_t;
+      fpb::k_imma_gemv_tma_t_p<<<std::min<uint32_t>((uint32_t)h->sm_count, nitems),
+                                 (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes, h->stream>>>(
+          h->tm_s, (uint32_t)h->n, reinterpret_cast<const uint32_t*>(h->d_slices), h->ttiles,
+          h->ptps_t, h->psplits_t, nitems, h->d_part, h->part_stride);
+      used = h->psplits_t;
+    } else {
+      dim3 grid(h->nstages_s, h->ttsplits);
+      fpb::k_imma_gemv_tma_t<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
+                               h->stream>>>(h->tm_s, (uint32_t)h->n,
+                                            reinterpret_cast<const uint32_t*>(h->d_slices),
+                                            h->ttiles, h->ttps, h->d_part, h->part_stride);
+    }
     if (h->time_gemv) cudaEventRecord(h->kev[3], h->stream);
     h->launches += 2;
-    return h->ttsplits;
+    return used;
   }
   const uint8_t* G = snp_major ? h->d_gs : h->d_gi;
   const uint64_t pitch = snp_major ? h->pitch_s : h->pitch_i;
@@ -730,6 +793,15 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
       if (h->time_gemv) cudaEventRecord(h->kev[snp ? 1 : 3], h->stream);
     }
   } stop_timer{h, snp_major};
+  if (h->use_tma && snp_major && h->persist_s) {
+    const uint32_t ntile = (rows + fpb::kTmaRows - 1) / fpb::kTmaRows;
+    const uint32_t nitems = ntile * h->psplits_s;
+    fpb::k_imma_gemv_tma_p<<<std::min<uint32_t>((uint32_t)h->sm_count, nitems),
+                             (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes, h->stream>>>(
+        h->tm_s, rows, h->d_slices, h->nstages_s, h->psps_s, h->psplits_s, nitems, h->d_part,
+        h->part_stride);
+    return h->psplits_s;
+  }
   if (h->use_tma) {
     const uint32_t nstages = snp_major ? h->nstages_s : h->nstages_i;
     const uint32_t splits = snp_major ? h->tsplits_s : h->tsplits_i;

@@ -753,6 +753,270 @@ k_imma_gemv_tma_t(const __grid_constant__ TmaDesc tmap, uint32_t C /* output len
 }
 
 // ---------------------------------------------------------------------------
+// Persistent forms of the two TMA contraction kernels.  One CTA per SM walks a
+// static round-robin list of work items (item = one tile of the output x one
+// split of the reduction axis); the TMA ring keeps running across items, so the
+// pipeline is filled once per launch instead of once per CTA and there is no
+// partial last wave (the one-item-per-CTA grids above lose ~4 % to each).
+// Same fragment mapping, fences and output layout as the kernels above.
+// Items are numbered tile-fastest (item = split x ntiles + tile), like blockIdx.x of the grids
+// above: CTAs that run side by side then read neighbouring 128-byte columns of the same rows
+// (second half) -- whole DRAM pages between them; split-fastest numbering cost 45 % there.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
+k_imma_gemv_tma_p(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* __restrict__ S,
+                  uint32_t nstages, uint32_t stages_per_split, uint32_t nsplits, uint32_t nitems,
+                  double* __restrict__ out, uint64_t out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kTmaStages * kTmaStageBytes;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < kTmaStages; i++) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (kTmaStages + i), kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumerWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+      uint32_t slot = 0, round = 0;
+      for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const uint32_t rt = item % (nitems / nsplits), sp = item / (nitems / nsplits);
+        const uint32_t s_begin = sp * stages_per_split;
+        const uint32_t s_end = min(nstages, s_begin + stages_per_split);
+        for (uint32_t st = s_begin; st < s_end; st++) {
+          const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTmaStages + slot);
+          if (round > 0) mbar_wait(empty, (round - 1) & 1);
+          const uint32_t dst = base + slot * kTmaStageBytes;
+          mbar_expect_tx(full, kTmaStageBytes);
+          tma_load_2d(dst, &tmap, (int)(st * kTmaStageCols), (int)(rt * kTmaRows), full, pol_stream);
+          bulk_load(dst + kTmaTileBytes, S + (uint64_t)st * (kTmaSliceBytes / 16), kTmaSliceBytes,
+                    full, pol_keep);
+          if (++slot == kTmaStages) {
+            slot = 0;
+            round++;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  const int g = lane >> 2, q = lane & 3;
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  uint32_t roff[2][2];
+#pragma unroll
+  for (int t = 0; t < 2; t++)
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) roff[t][hf] = (uint32_t)(warp * 32 + t * 16 + hf * 8 + rho) * 128u;
+  const uint32_t rx = (uint32_t)(rho & 7);
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+  uint32_t slot = 0, round = 0;
+  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const uint32_t rt = item % (nitems / nsplits), sp = item / (nitems / nsplits);
+    const uint32_t s_begin = sp * stages_per_split;
+    const uint32_t s_end = min(nstages, s_begin + stages_per_split);
+    int acc[2][2][4] = {};
+    double dacc[2][4] = {};
+    for (uint32_t st = s_begin; st < s_end; st++) {
+      mbar_wait(bars + 8 * slot, round & 1);
+      const uint32_t tile = base + slot * kTmaStageBytes;
+      const uint32_t sl = tile + kTmaTileBytes;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t chunk = ((uint32_t)(u * 4 + q) ^ rx) << 4;
+        uint4 w[2][2];
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(w[t][hf].x), "=r"(w[t][hf].y), "=r"(w[t][hf].z), "=r"(w[t][hf].w)
+                         : "r"(tile + roff[t][hf] + chunk));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int wl = u * 16 + q * 4 + j;
+          uint4 bv;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(bv.x), "=r"(bv.y), "=r"(bv.z), "=r"(bv.w)
+                       : "r"(sl + (uint32_t)slice_slot(wl, g) * 16u));
+#pragma unroll
+          for (int t = 0; t < 2; t++) {
+            const uint32_t xa = j == 0 ? w[t][0].x : j == 1 ? w[t][0].y : j == 2 ? w[t][0].z : w[t][0].w;
+            const uint32_t xb = j == 0 ? w[t][1].x : j == 1 ? w[t][1].y : j == 2 ? w[t][1].z : w[t][1].w;
+            mma_u8s8(acc[t][0], xa & 0x03030303u, xb & 0x03030303u, xa & 0x0F0F0F0Fu,
+                     xb & 0x0F0F0F0Fu, bv.x, bv.y);
+            mma_u8s8(acc[t][1], xa & 0x3F3F3F3Fu, xb & 0x3F3F3F3Fu, xa, xb, bv.z, bv.w);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // see k_imma_gemv_tma
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (kTmaStages + slot));
+      if (++slot == kTmaStages) {
+        slot = 0;
+        round++;
+      }
+      if (((st - s_begin) % kTmaFlushStages) == kTmaFlushStages - 1) {
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            dacc[t][k] += (double)acc[t][0][k] + (double)acc[t][1][k];
+            acc[t][0][k] = 0;
+            acc[t][1][k] = 0;
+          }
+      }
+    }
+    double* o = out + (uint64_t)sp * out_stride;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[t][k] += (double)acc[t][0][k] + (double)acc[t][1][k];
+      double ra = dacc[t][0] * w0 + dacc[t][1] * w1;
+      double rb = dacc[t][2] * w0 + dacc[t][3] * w1;
+      ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+      ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+      if (q == 0) {
+        const uint32_t r = rt * kTmaRows + warp * 32 + t * 16 + rho;
+        if (r < R) o[r] = ra;
+        if (r + 8 < R) o[r + 8] = rb;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
+k_imma_gemv_tma_t_p(const __grid_constant__ TmaDesc tmap, uint32_t C /* output length */,
+                    const uint32_t* __restrict__ S, uint32_t ntiles, uint32_t tiles_per_split,
+                    uint32_t nsplits, uint32_t nitems, double* __restrict__ out,
+                    uint64_t out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kTmaStages * kTmaTStageBytes;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < kTmaStages; i++) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (kTmaStages + i), kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumerWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+      uint32_t slot = 0, round = 0;
+      for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const uint32_t cs = item % (nitems / nsplits), sp = item / (nitems / nsplits);
+        const uint32_t t_begin = sp * tiles_per_split;
+        const uint32_t t_end = min(ntiles, t_begin + tiles_per_split);
+        for (uint32_t tt = t_begin; tt < t_end; tt++) {
+          const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTmaStages + slot);
+          if (round > 0) mbar_wait(empty, (round - 1) & 1);
+          const uint32_t dst = base + slot * kTmaTStageBytes;
+          mbar_expect_tx(full, kTmaTStageBytes);
+          tma_load_2d(dst, &tmap, (int)(cs * kTmaStageCols), (int)(tt * kTmaRows), full, pol_stream);
+          bulk_load(dst + kTmaTileBytes, S + (uint64_t)tt * (kTmaTSliceBytes / 4), kTmaTSliceBytes,
+                    full, pol_keep);
+          if (++slot == kTmaStages) {
+            slot = 0;
+            round++;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  const int g = lane >> 2, q = lane & 3;
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+  uint32_t slot = 0, round = 0;
+  for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const uint32_t cs = item % (nitems / nsplits), sp = item / (nitems / nsplits);
+    const uint32_t t_begin = sp * tiles_per_split;
+    const uint32_t t_end = min(ntiles, t_begin + tiles_per_split);
+    int acc[4][4] = {};
+    double dacc[4][4] = {};
+    for (uint32_t tt = t_begin; tt < t_end; tt++) {
+      mbar_wait(bars + 8 * slot, round & 1);
+      const uint32_t tile = base + slot * kTmaTStageBytes;
+      const uint32_t sl = tile + kTmaTileBytes;
+#pragma unroll
+      for (int ks = 0; ks < kTmaRows / 32; ks++) {
+        const uint32_t row = (uint32_t)(ks * 32 + lane);
+        const uint32_t addr = tile + row * 128u + ((((uint32_t)warp) ^ (row & 7u)) << 4);
+        uint32_t a0, a1, a2, a3, b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(addr));
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
+                     : "=r"(b0), "=r"(b1)
+                     : "r"(sl + (uint32_t)(((ks * 8 + g) * 4 + q) * 8)));
+        mma_u8s8(acc[0], a0 & 0x03030303u, a1 & 0x03030303u, a2 & 0x03030303u, a3 & 0x03030303u, b0, b1);
+        mma_u8s8(acc[1], a0 & 0x0F0F0F0Fu, a1 & 0x0F0F0F0Fu, a2 & 0x0F0F0F0Fu, a3 & 0x0F0F0F0Fu, b0, b1);
+        mma_u8s8(acc[2], a0 & 0x3F3F3F3Fu, a1 & 0x3F3F3F3Fu, a2 & 0x3F3F3F3Fu, a3 & 0x3F3F3F3Fu, b0, b1);
+        mma_u8s8(acc[3], a0, a1, a2, a3, b0, b1);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // see k_imma_gemv_tma
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (kTmaStages + slot));
+      if (++slot == kTmaStages) {
+        slot = 0;
+        round++;
+      }
+      if (((tt - t_begin) % kTmaFlushStages) == kTmaFlushStages - 1) {
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            dacc[f][k] += (double)acc[f][k];
+            acc[f][k] = 0;
+          }
+      }
+    }
+    double* o = out + (uint64_t)sp * out_stride;
+    const uint64_t byte_a = (uint64_t)cs * kTmaStageCols + warp * 16 + g;
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[f][k] += (double)acc[f][k];
+#pragma unroll
+    for (int f = 3; f > 0; f--)  // cumulative -> per field (integers below 2^53: exact)
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[f][k] -= dacc[f - 1][k];
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const double sf = ldexp(1.0, -2 * f);
+      double ra = (dacc[f][0] * w0 + dacc[f][1] * w1) * sf;
+      double rb = (dacc[f][2] * w0 + dacc[f][3] * w1) * sf;
+      ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+      ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+      if (q == 0) {
+        const uint64_t ia = byte_a * 4 + f, ib = (byte_a + 8) * 4 + f;
+        if (ia < C) o[ia] = ra;
+        if (ib < C) o[ib] = rb;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Sparse missing-genotype sums  out[r] = sum_{c in row r} vec[c].
 //
 // A plain CSR gather is bound by L2 sector traffic (every 8-byte read of `vec`

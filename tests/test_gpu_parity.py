@@ -591,3 +591,28 @@ def test_fused_at_full_width(native_lib, fused, monkeypatch):
     two = s.create_operator()
     assert not _is_fused(two)                  # default path
     assert _relerr(y, two.perform_op(x)) <= 1e-13
+
+
+def test_persistent_and_one_shot_grids_agree(native_lib, monkeypatch):
+    """Small grids use the persistent TMA kernels (one CTA per SM walks a work
+    list), large ones the one-item-per-CTA grids; FPB_PERSIST=0|1 forces the
+    choice.  Same items, same sums (the split counts differ, hence ~1e-15
+    differences)."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    monkeypatch.delenv("FPB_GEMV", raising=False)
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(70001, 3001, seed=7, missing_rate=0.004)
+    rng = np.random.default_rng(3)
+    x, v = rng.standard_normal(s.n), rng.standard_normal(s.p)
+    monkeypatch.setenv("FPB_PERSIST", "1")
+    a = s.create_operator()
+    ya, ta, za = a.perform_op(x), a.crossprod(x), a.prod(v)
+    assert np.array_equal(a.perform_op(x), ya)
+    monkeypatch.setenv("FPB_PERSIST", "0")
+    b = s.create_operator()
+    assert _relerr(b.perform_op(x), ya) <= 1e-13
+    assert _relerr(b.crossprod(x), ta) <= 1e-13
+    assert _relerr(b.prod(v), za) <= 1e-13
+    orc = O.COracle(s.packed_bed(0, 64), s.n, 64)
+    sub = s.create_operator(j0=0, j1=64)
+    assert _relerr(sub.perform_op(x), orc.perform_op(x, 0)) <= OP_RTOL
