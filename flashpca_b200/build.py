@@ -64,9 +64,28 @@ def build_cli(force: bool = False) -> str:
     return CLI
 
 
+RAPI = os.path.join(HERE, "rapi_check")
+
+
+def build_rapi_check(force: bool = False) -> str:
+    """Test driver for the flashpcaR entry points (host/flashpcar.hpp)."""
+    host = os.path.join(HERE, "host")
+    cpps = [os.path.join(host, f) for f in sorted(os.listdir(host))
+            if f.endswith(".cpp") and f != "flashpca.cpp"]
+    main = os.path.join(host, "rapi", "rapi_check.cpp")
+    hdrs = [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".hpp")]
+    if not force and _newer(RAPI, cpps + hdrs + [main, LIB]):
+        return RAPI
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"),
+           "-o", RAPI, main, *cpps, "-L", HERE, "-lflashpca_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return RAPI
+
+
 def build_all(force: bool = False) -> None:
     build_lib(force)
     build_cli(force)
+    build_rapi_check(force)
 
 
 if __name__ == "__main__":

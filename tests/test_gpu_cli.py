@@ -136,3 +136,50 @@ def test_nccl_sharded_two_gpus():
                           "29617", script], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "NCCL_SHARD_OK" in out.stdout
+
+
+@pytest.mark.parametrize("mode,stand,divisor", [("plink", 3, 2), ("plink", 2, 1), ("matrix", 3, 2),
+                                                ("matrix", 1, 2), ("matrix", 0, 0)])
+def test_flashpcar_entry_points(mode, stand, divisor, tmp_path):
+    """flashpca_plink_internal / flashpca_internal (flashpcaR/src/flashpca.cpp:17-197)
+    as plain C++ (host/flashpcar.hpp): same parameter lists and named result fields;
+    checked like flashpcaR/tests/testthat/test_pca.R:45-105 against the dense
+    eigendecomposition of the oracle-standardised matrix."""
+    import json
+    from flashpca_b200 import build
+    build.build_lib()
+    exe = build.build_rapi_check()
+    stem = FIXTURES["data_chr1"]
+    ndim = 6
+    out = subprocess.run([exe, mode, stem, str(ndim), str(stand), str(divisor), "1", "1"],
+                         capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr
+    res = json.loads(out.stdout)
+    _, payload, n, p = load_fixture("data_chr1")
+    x = O.dosage_matrix(O.dense_codes(payload, n, p))
+    s_ref, msd = O.standardise_matrix(x, stand)
+    div = {0: 1.0, 1: n - 1.0, 2: float(p)}[divisor]
+    w, v = np.linalg.eigh(s_ref @ s_ref.T / div)
+    d_ref, u_ref = w[::-1][:ndim], v[:, ::-1][:, :ndim]
+    d = np.array(res["values"])
+    assert np.abs(d / d_ref - 1).max() < 1e-6
+    mat = lambda m: np.array(m["data"]).reshape(m["ncol"], m["nrow"]).T
+    u = O.sign_align(mat(res["vectors"]), u_ref)
+    assert np.abs(u - u_ref).max() < 1e-6
+    px = mat(res["projection"])
+    assert np.abs(np.abs(px) - np.abs(u_ref * np.sqrt(d_ref))).max() < 1e-6 * np.abs(px).max()
+    trace = np.sum(s_ref * s_ref) / div
+    assert np.abs(np.array(res["pve"]) / (d_ref / trace) - 1).max() < 1e-6
+    vload = mat(res["loadings"])
+    vref = s_ref.T @ u_ref / np.sqrt(d_ref) / np.sqrt(div)
+    assert np.abs(O.sign_align(vload, vref) - vref).max() < 1e-6 * np.abs(vref).max()
+    if stand != 0:      # return_scale: center / scale = per-SNP mean / sd (flashpca.cpp:46-52)
+        assert np.allclose(res["center"], msd[:, 0], rtol=1e-12, atol=1e-13)
+        assert np.allclose(res["scale"], msd[:, 1], rtol=1e-12, atol=1e-13)
+    else:
+        assert res["center"] == [] and res["scale"] == []
+    if mode == "plink":  # rownames "FID:IID" in fam order (flashpca.cpp:147-155)
+        fid, iid = O.read_fam_ids(stem + ".fam")
+        assert res["rownames"] == [a + ":" + b for a, b in zip(fid, iid)]
+    else:
+        assert res["rownames"] == []
