@@ -135,6 +135,9 @@ struct fpb_handle {
   // persistent forms of the two TMA kernels: used per half when the one-item-per-CTA grid would have
   // fewer than ~10 waves (pipeline fill and the partial last wave then dominate); FPB_PERSIST=0|1 forces
   bool persist_s = false, persist_t = false;
+  // wide-stripe second half (k_imma_gemv_tma_tw): 256-byte stripes, 128-row stages
+  bool wide_t = false;
+  uint32_t wtiles = 0, wsplits = 1, wtps = 1, wstripes = 0;
   uint32_t psplits_s = 1, psps_s = 1, psplits_t = 1, ptps_t = 1;
   // fused single-pass perform_op (fpb_fused.cuh)
   bool use_fused = false;
@@ -483,7 +486,6 @@ int setup_fused(fpb_handle* h) {
   if (const char* pv = getenv("FPB_FUSED_POL1")) h->f_pol1 = (uint32_t)atoi(pv);
   if (const char* pv = getenv("FPB_FUSED_POL2")) h->f_pol2 = (uint32_t)atoi(pv);
   if (const char* pv = getenv("FPB_FUSED_PREFETCH")) h->f_prefetch = (uint32_t)std::max(0, atoi(pv));
-  if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_f, fpb::kFRows)) return 1;
   FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_fused_op, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpb::kFSmemBytes));
   const size_t part_bytes = sizeof(double) * (size_t)fpb::kFASlots * fpb::kFRows * h->f_gpad;
@@ -656,7 +658,22 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        fpb::kTmaSmemBytes));
     }
-    if (h->single_copy && setup_fused(h)) return 1;
+    if (h->single_copy) {
+      if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_f, fpb::kFRows)) return 1;
+      FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma_tw,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fpb::kTmaSmemBytes));
+      // wide-stripe second half: same SNP ranges per split as the narrow kernel
+      const char* wv = getenv("FPB_P2WIDE");
+      h->wstripes = (uint32_t)((h->pitch_s + 255) / 256);
+      h->wtiles = (uint32_t)((h->nsnps + fpb::kTmaWRows - 1) / fpb::kTmaWRows);
+      h->wtps = 2 * h->ttps;
+      h->wsplits = (h->wtiles + h->wtps - 1) / h->wtps;
+      // measured at 500k x 100k: 1.94 ms vs 1.93 ms for the 128-byte stripes (profiles/
+      // r01_wide_sweep.txt) -- no gain, so it is a variant (FPB_P2WIDE=1), not the default
+      h->wide_t = wv && atoi(wv) == 1;
+      if (setup_fused(h)) return 1;
+    }
   }
   uint64_t max_chunks = std::max(h->nchunks_s, h->nchunks_i);
   // the K-major slices of the single-copy second half need 8 bytes per SNP, padded to whole tiles
@@ -668,7 +685,7 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
                              std::max(std::max(std::max(std::max(h->splits_s, h->splits_i),
                                                         std::max(h->tsplits_s, h->tsplits_i)),
                                                h->ttsplits),
-                                      std::max(h->psplits_s, h->psplits_t))));
+                                      std::max(std::max(h->psplits_s, h->psplits_t), h->wsplits))));
   FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * h->nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * h->nsnps));
   const size_t max_parts = std::max<size_t>(kVecBlocks, (h->nsnps + 255) / 256);
@@ -759,7 +776,14 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
         reinterpret_cast<uint32_t*>(h->d_slices));
     if (h->time_gemv) cudaEventRecord(h->kev[2], h->stream);
     uint32_t used = h->ttsplits;
-    if (h->persist_t) {
+    if (h->wide_t) {
+      dim3 grid(h->wstripes, h->wsplits);
+      fpb::k_imma_gemv_tma_tw<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
+                                h->stream>>>(h->tm_f, (uint32_t)h->n,
+                                             reinterpret_cast<const uint32_t*>(h->d_slices),
+                                             h->wtiles, h->wtps, h->d_part, h->part_stride);
+      used = h->wsplits;
+    } else if (h->persist_t) {
       const uint32_t nitems = h->nstages_s * h->psplits_t;
       fpb::k_imma_gemv_tma_t_p<<<std::min<uint32_t>((uint32_t)h->sm_count, nitems),
                                  (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes, h->stream>>>(

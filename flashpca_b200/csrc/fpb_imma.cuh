@@ -753,6 +753,139 @@ k_imma_gemv_tma_t(const __grid_constant__ TmaDesc tmap, uint32_t C /* output len
 }
 
 // ---------------------------------------------------------------------------
+// Second half, wide-stripe form.  A CTA owns a 256-byte column stripe (1024
+// individuals): each stage holds two [128 rows x 128 B] boxes that are adjacent
+// in memory, so every SNP row is read in 256-byte runs (k_imma_gemv_tma_t reads
+// 128-byte runs and relies on the neighbouring CTA for the other half of the
+// DRAM burst), the B fragments are shared by the two boxes, and a CTA walks
+// twice as many stages (half the pipeline-fill overhead per byte).
+// ---------------------------------------------------------------------------
+constexpr int kTmaWRows = 128;
+constexpr int kTmaWBoxBytes = kTmaWRows * 128;                           // 16 KB
+constexpr int kTmaWSliceBytes = (kTmaWRows / 32) * 256;                  // 1 KB
+constexpr int kTmaWStageBytes = 2 * kTmaWBoxBytes + kTmaWSliceBytes;     // 33 KB
+static_assert(kTmaStages * kTmaWStageBytes + 1024 + 128 <= kTmaSmemBytes, "ring too large");
+constexpr int kTmaWFlushStages = 192;                                    // 24576 SNP rows
+
+__global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
+k_imma_gemv_tma_tw(const __grid_constant__ TmaDesc tmap /* box 128 B x 128 rows */, uint32_t C,
+                   const uint32_t* __restrict__ S, uint32_t ntiles, uint32_t tiles_per_split,
+                   double* __restrict__ out, uint64_t out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kTmaStages * kTmaWStageBytes;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t t_begin = blockIdx.y * tiles_per_split;
+  const uint32_t t_end = min(ntiles, t_begin + tiles_per_split);
+  const uint32_t nst = t_end > t_begin ? t_end - t_begin : 0;
+  const uint32_t xbyte0 = blockIdx.x * 256u;
+
+  if (tid == 0) {
+    for (int i = 0; i < kTmaStages; i++) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (kTmaStages + i), kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumerWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+      for (uint32_t it = 0; it < nst; it++) {
+        const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+        const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTmaStages + slot);
+        if (round > 0) mbar_wait(empty, (round - 1) & 1);
+        const uint32_t dst = base + slot * kTmaWStageBytes;
+        mbar_expect_tx(full, kTmaWStageBytes);
+        const int y = (int)((t_begin + it) * kTmaWRows);
+        tma_load_2d(dst, &tmap, (int)xbyte0, y, full, pol_stream);
+        tma_load_2d(dst + kTmaWBoxBytes, &tmap, (int)xbyte0 + 128, y, full, pol_stream);
+        bulk_load(dst + 2 * kTmaWBoxBytes, S + (uint64_t)(t_begin + it) * (kTmaWSliceBytes / 4),
+                  kTmaWSliceBytes, full, pol_keep);
+      }
+    }
+    return;
+  }
+
+  const int g = lane >> 2, q = lane & 3;
+  int acc[2][4][4] = {};       // [box][field (cumulative)][frag]
+  double dacc[2][4][4] = {};
+  for (uint32_t it = 0; it < nst; it++) {
+    const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+    mbar_wait(bars + 8 * slot, round & 1);
+    const uint32_t tile = base + slot * kTmaWStageBytes;
+    const uint32_t sl = tile + 2 * kTmaWBoxBytes;
+#pragma unroll
+    for (int ks = 0; ks < kTmaWRows / 32; ks++) {
+      const uint32_t row = (uint32_t)(ks * 32 + lane);
+      const uint32_t addr = tile + row * 128u + ((((uint32_t)warp) ^ (row & 7u)) << 4);
+      uint32_t b0, b1;
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
+                   : "=r"(b0), "=r"(b1)
+                   : "r"(sl + (uint32_t)(((ks * 8 + g) * 4 + q) * 8)));
+#pragma unroll
+      for (int bx = 0; bx < 2; bx++) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(addr + (uint32_t)bx * kTmaWBoxBytes));
+        mma_u8s8(acc[bx][0], a0 & 0x03030303u, a1 & 0x03030303u, a2 & 0x03030303u, a3 & 0x03030303u, b0, b1);
+        mma_u8s8(acc[bx][1], a0 & 0x0F0F0F0Fu, a1 & 0x0F0F0F0Fu, a2 & 0x0F0F0F0Fu, a3 & 0x0F0F0F0Fu, b0, b1);
+        mma_u8s8(acc[bx][2], a0 & 0x3F3F3F3Fu, a1 & 0x3F3F3F3Fu, a2 & 0x3F3F3F3Fu, a3 & 0x3F3F3F3Fu, b0, b1);
+        mma_u8s8(acc[bx][3], a0, a1, a2, a3, b0, b1);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // see k_imma_gemv_tma
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8 * (kTmaStages + slot));
+    if ((it % kTmaWFlushStages) == kTmaWFlushStages - 1) {
+#pragma unroll
+      for (int bx = 0; bx < 2; bx++)
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            dacc[bx][f][k] += (double)acc[bx][f][k];
+            acc[bx][f][k] = 0;
+          }
+    }
+  }
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+  double* o = out + (uint64_t)blockIdx.y * out_stride;
+#pragma unroll
+  for (int bx = 0; bx < 2; bx++) {
+    const uint64_t byte_a = (uint64_t)xbyte0 + bx * 128 + warp * 16 + g;
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[bx][f][k] += (double)acc[bx][f][k];
+#pragma unroll
+    for (int f = 3; f > 0; f--)  // cumulative -> per field (integers below 2^53: exact)
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[bx][f][k] -= dacc[bx][f - 1][k];
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const double sf = ldexp(1.0, -2 * f);
+      double ra = (dacc[bx][f][0] * w0 + dacc[bx][f][1] * w1) * sf;
+      double rb = (dacc[bx][f][2] * w0 + dacc[bx][f][3] * w1) * sf;
+      ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+      ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+      if (q == 0) {
+        const uint64_t ia = byte_a * 4 + f, ib = (byte_a + 8) * 4 + f;
+        if (ia < C) o[ia] = ra;
+        if (ib < C) o[ib] = rb;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Persistent forms of the two TMA contraction kernels.  One CTA per SM walks a
 // static round-robin list of work items (item = one tile of the output x one
 // split of the reduction axis); the TMA ring keeps running across items, so the

@@ -193,7 +193,7 @@ def test_tensor_path_is_deterministic_and_default(native_lib, monkeypatch):
     assert np.isnan(op.perform_op(np.full(n, np.nan))).all()
 
 
-@pytest.mark.parametrize("variant", ["tma", "tma2", "ldg"])
+@pytest.mark.parametrize("variant", ["tma", "tma2", "ldg", "wide", "narrow"])
 def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
     """FPB_GEMV selects the contraction kernels: default single-copy TMA pipeline
     (k_imma_gemv_tma + k_imma_gemv_tma_t), two-copy TMA (tma2) and the register-staged
@@ -207,7 +207,14 @@ def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
     rng = np.random.default_rng(31)
     x, v = rng.standard_normal(n), rng.standard_normal(p)
     y0, t0, z0 = base.perform_op(x), base.crossprod(x), base.prod(v)
-    monkeypatch.setenv("FPB_GEMV", variant)
+    if variant == "wide":       # second half with 256-byte stripes (k_imma_gemv_tma_tw)
+        monkeypatch.setenv("FPB_P2WIDE", "1")
+        monkeypatch.setenv("FPB_PERSIST", "0")
+    elif variant == "narrow":   # one-shot 128-byte stripe grids
+        monkeypatch.setenv("FPB_P2WIDE", "0")
+        monkeypatch.setenv("FPB_PERSIST", "0")
+    else:
+        monkeypatch.setenv("FPB_GEMV", variant)
     op = _mk(payload, n, p)
     y1 = op.perform_op(x)
     assert _relerr(y1, y0) <= 1e-13
