@@ -632,7 +632,10 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
       const uint32_t ntile_s = (uint32_t)((h->nsnps + fpb::kTmaRows - 1) / fpb::kTmaRows);
       const uint32_t few = 10u * (uint32_t)h->sm_count;
       h->persist_s = h->single_copy && (pv ? atoi(pv) != 0 : ntile_s * h->tsplits_s < few);
-      h->persist_t = h->single_copy && (pv ? atoi(pv) != 0 : h->nstages_s * h->ttsplits < few);
+      // second half: only with few column stripes (small N); with many stripes the persistent
+      // CTAs run in lockstep over the SNP rows and lose DRAM efficiency (8-GPU shard 500k x 12.5k:
+      // 0.345 vs 0.275 ms, profiles/r01_scaling_persist.txt)
+      h->persist_t = h->single_copy && (pv ? atoi(pv) != 0 : h->nstages_s < (uint32_t)h->sm_count);
       if (h->persist_s) {
         pick_splits_persist(ntile_s, h->nstages_s, h->sm_count, &h->psplits_s, &h->psps_s);
         override_splits("FPB_DEBUG_SPLITS1", h->nstages_s, &h->psplits_s, &h->psps_s);
