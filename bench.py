@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=20, help="ndim of the solve")
     ap.add_argument("--no-solve", action="store_true", help="skip the full k=20 solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the 10k x 100k side measurement")
     ap.add_argument("--cpu-sample-snps", type=int, default=0)
     return ap.parse_args()
 
@@ -344,6 +345,33 @@ def run_b200(a):
                                "roofline fraction is capped near 0.55"},
       }
 
+    # BASELINE.json configs[1] (synthetic 10,000 x 100,000, k=20, one GPU) next to the headline
+    # configuration: same metric, device-resident vectors, CUDA events
+    small = None
+    if world == 1 and (n, p) == (500000, 100000) and not a.no_small:
+        sn, sp_ = 10000, 100000
+        sspec = SynthSpec(sn, sp_)
+        sop = sspec.create_operator(device=local)
+        sx = torch.randn(sn, dtype=torch.float64, device="cuda")
+        sy = torch.empty_like(sx)
+        _lib.check(lib.fpb_time_perform_op(sop.h, sx.data_ptr(), sy.data_ptr(), 10,
+                                           ctypes.byref(ms), None), sop.h)
+        _lib.check(lib.fpb_time_perform_op(sop.h, sx.data_ptr(), sy.data_ptr(), 200,
+                                           ctypes.byref(ms), kms), sop.h)
+        s_ms = ms.value
+        s_alg = ((sn + 3) // 4) * sp_ + 16 * sn + 16 * sp_
+        t0 = time.perf_counter()
+        sres = sop.pca(k, 2 * k + 1, 500, 1e-6)
+        s_solve = time.perf_counter() - t0
+        small = {"workload": "synthetic Balding-Nichols bed %d x %d, k=%d (BASELINE configs[1])"
+                             % (sn, sp_, k),
+                 "value": sn * sp_ / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms,
+                 "contraction_launch_ms": [kms[2], kms[3]],
+                 "perform_op_frac_of_single_read_roofline": s_alg / (s_ms * 1e-3) / 1e9 / peak,
+                 "solve_seconds_first_call": s_solve, "solve_nops": int(sres["nops"]),
+                 "note": "250 MB matrix: two HBM passes + 9 launches per op; launch-bound"}
+        sop.close()
+
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         snps = a.cpu_sample_snps or max(64, min(p, int(1e9 // n)))
@@ -381,6 +409,7 @@ def run_b200(a):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "solve": solve,
+        "config_10k_x_100k": small,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
