@@ -21,6 +21,7 @@ SIGNATURES = {
     "fpb_last_error": (_c.c_char_p, [_vp]),
     "fpb_create": (_i, [_c.POINTER(_vp), _vp, _u64, _u64, _i, _vp, _i]),
     "fpb_create_from_file": (_i, [_c.POINTER(_vp), _c.c_char_p, _u64, _u64, _u64, _i, _vp, _i]),
+    "fpb_create_streaming": (_i, [_c.POINTER(_vp), _c.c_char_p, _u64, _u64, _u64, _u64, _i, _vp, _i]),
     "fpb_create_synthetic": (_i, [_c.POINTER(_vp), _u64, _u64, _u64, _vp, _vp, _u32, _u32, _u64,
                                   _i, _i]),
     "fpb_create_dense": (_i, [_c.POINTER(_vp), _vp, _u64, _u64, _i, _i]),
@@ -53,11 +54,12 @@ SIGNATURES = {
     "fpb_time_perform_op": (_i, [_vp, _vp, _vp, _u32, _c.POINTER(_c.c_float), _vp]),
     "fpb_launch_count": (_u64, [_vp]),
     "fpb_path_info": (_c.c_uint, [_vp]),
+    "fpb_device_memory": (_i, [_i, _c.POINTER(_u64), _c.POINTER(_u64)]),
     "fpb_fused_debug": (_i, [_vp, _vp, _u64]),
 }
 
 # fpb_path_info bits (include/flashpca_b200.h)
-PATH_DENSE, PATH_TENSOR, PATH_TMA, PATH_SINGLE_COPY, PATH_FUSED = 1, 2, 4, 8, 16
+PATH_DENSE, PATH_TENSOR, PATH_TMA, PATH_SINGLE_COPY, PATH_FUSED, PATH_STREAMING = 1, 2, 4, 8, 16, 32
 
 _lib = None
 

@@ -148,6 +148,17 @@ struct fpb_handle {
   uint32_t* d_fsync = nullptr;             // watchdog error word
   unsigned long long* d_fdbg = nullptr;    // FPB_FUSED_DEBUG: time stamps of two CTAs
   bool fused_used = false;                 // an op ran through the fused kernel since the last check
+  // out-of-HBM streaming (fpb_create_streaming): the parent owns SNP slabs ("kids": ordinary
+  // handles whose genotypes live in pinned host memory), two device slab buffers and a copy stream
+  std::vector<fpb_handle*> kids;
+  std::vector<uint8_t*> kid_host;          // pinned recoded genotypes of each kid (pitch_s x nsnps_kid)
+  std::vector<uint64_t> kid_off;           // first SNP of each kid
+  uint8_t* sbuf[2] = {nullptr, nullptr};
+  fpb::TmaDesc tm_s_alt[2], tm_f_alt[2];   // kid: tensor maps over the parent's two slab buffers
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  double* d_ytmp = nullptr;
+  bool borrowed = false;                   // kid: streams and d_gs belong to the parent
   // host-pointer API staging (grown on demand)
   double* d_in = nullptr;
   double* d_out = nullptr;
@@ -978,6 +989,11 @@ void fused_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
 // The fused kernel reports a timed-out wait (a protocol failure) through a device
 // word instead of hanging; surfaced at the API's synchronisation points.
 int check_fused(fpb_handle* h) {
+  for (fpb_handle* kid : h->kids)
+    if (check_fused(kid)) {
+      h->err = kid->err;
+      return 1;
+    }
   if (!h->fused_used) return 0;
   h->fused_used = false;
   uint32_t code = 0;
@@ -1008,7 +1024,12 @@ void dense_prod(fpb_handle* h, const double* d_v, double* d_y) {
 }
 
 // t (nsnps) = X' x
+void streaming_crossprod(fpb_handle* h, const double* d_x, double* d_t);
+void streaming_prod(fpb_handle* h, const double* d_v, double* d_y);
+void streaming_perform_op(fpb_handle* h, const double* d_x, double* d_y);
+
 void launch_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
+  if (!h->kids.empty()) return streaming_crossprod(h, d_x, d_t);
   if (h->dense) dense_crossprod(h, d_x, d_t);
   else if (h->use_imma) imma_crossprod(h, d_x, d_t, false);
   else generic_crossprod(h, d_x, d_t);
@@ -1016,6 +1037,7 @@ void launch_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
 
 // y (N) = X v
 void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
+  if (!h->kids.empty()) return streaming_prod(h, d_v, d_y);
   if (h->dense) {
     dense_prod(h, d_v, d_y);
   } else if (h->use_imma) {
@@ -1032,6 +1054,7 @@ void launch_prod(fpb_handle* h, const double* d_v, double* d_y) {
 
 // y (N) = X X' x
 void launch_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
+  if (!h->kids.empty()) return streaming_perform_op(h, d_x, d_y);
   if (h->dense) {  // y = mat * (mat' x), svdwide.cpp:10
     dense_crossprod(h, d_x, h->d_t);
     dense_prod(h, h->d_t, d_y);
@@ -1058,6 +1081,68 @@ int allreduce(fpb_handle* h, double* d_buf, size_t count) {
 int check_launch(fpb_handle* h) {
   FPB_CUDA(h, cudaGetLastError());
   return 0;
+}
+
+
+// ------------------------------ out-of-HBM streaming -----------------------
+// y = sum_b X_b X_b' x over SNP slabs, the reference's own block loop (svdwide.cpp:48-59,
+// Data::read_snp_block per block) with the disk re-read replaced by a pinned-host -> HBM
+// copy that overlaps the previous slab's kernels.
+
+__global__ void k_axpy1(double* __restrict__ y, const double* __restrict__ t, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] += t[i];
+}
+
+// make slab b resident in buffer b & 1 (copy stream), order the compute stream behind it
+void stream_in(fpb_handle* h, size_t b) {
+  const int i = (int)(b & 1);
+  fpb_handle* kid = h->kids[b];
+  cudaStreamWaitEvent(h->copy, h->ev_done[i], 0);  // kernels of slab b - 2 are done with the buffer
+  cudaMemcpyAsync(h->sbuf[i], h->kid_host[b], kid->pitch_s * kid->nsnps, cudaMemcpyHostToDevice,
+                  h->copy);
+  cudaEventRecord(h->ev_copied[i], h->copy);
+  cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0);
+  kid->d_gs = h->sbuf[i];
+  kid->tm_s = kid->tm_s_alt[i];
+  kid->tm_f = kid->tm_f_alt[i];
+}
+void stream_done(fpb_handle* h, size_t b) {
+  cudaEventRecord(h->ev_done[b & 1], h->stream);
+  h->launches += h->kids[b]->launches;
+  h->kids[b]->launches = 0;
+}
+
+void streaming_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
+  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
+  for (size_t b = 0; b < h->kids.size(); b++) {
+    stream_in(h, b);
+    launch_perform_op(h->kids[b], d_x, b == 0 ? d_y : h->d_ytmp);
+    if (b > 0) {
+      k_axpy1<<<gb, 256, 0, h->stream>>>(d_y, h->d_ytmp, h->n);  // block order, like upstream
+      h->launches++;
+    }
+    stream_done(h, b);
+  }
+}
+void streaming_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
+  for (size_t b = 0; b < h->kids.size(); b++) {
+    stream_in(h, b);
+    launch_crossprod(h->kids[b], d_x, d_t + h->kid_off[b]);
+    stream_done(h, b);
+  }
+}
+void streaming_prod(fpb_handle* h, const double* d_v, double* d_y) {
+  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
+  for (size_t b = 0; b < h->kids.size(); b++) {
+    stream_in(h, b);
+    launch_prod(h->kids[b], d_v + h->kid_off[b], b == 0 ? d_y : h->d_ytmp);
+    if (b > 0) {
+      k_axpy1<<<gb, 256, 0, h->stream>>>(d_y, h->d_ytmp, h->n);
+      h->launches++;
+    }
+    stream_done(h, b);
+  }
 }
 
 }  // namespace
@@ -1146,6 +1231,105 @@ int fpb_create_from_file(fpb_handle** out, const char* bed_path, uint64_t n, uin
   }
   fclose(f);
   if (!rc) rc = finish_create(h, preloaded_meansd);
+  if (rc) {
+    g_err = h->err;
+    fpb_destroy(h);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+int fpb_create_streaming(fpb_handle** out, const char* bed_path, uint64_t n, uint64_t snp_begin,
+                         uint64_t snp_count, uint64_t snps_per_slab, int stand_method,
+                         const double* preloaded_meansd, int device) {
+  if (!out || !bed_path) FPB_FAIL((fpb_handle*)nullptr, "null argument");
+  *out = nullptr;
+  if (n == 0) FPB_FAIL((fpb_handle*)nullptr, "empty genotype matrix (N == 0 or nsnps == 0)");
+  if (snps_per_slab == 0) FPB_FAIL((fpb_handle*)nullptr, "snps_per_slab must be positive");
+  {
+    const char* gv = getenv("FPB_GEMV");
+    if (gv && (!strcmp(gv, "ldg") || !strcmp(gv, "tma2")))
+      FPB_FAIL((fpb_handle*)nullptr, "streaming mode needs the single-copy kernels (unset FPB_GEMV)");
+  }
+  FILE* f = fopen(bed_path, "rb");
+  if (!f)
+    FPB_FAIL((fpb_handle*)nullptr, std::string("[Data::read_bed] Error reading file ") + bed_path +
+                                       ", error " + strerror(errno));
+  fseeko(f, 0, SEEK_END);
+  const uint64_t fsz = (uint64_t)ftello(f);
+  fclose(f);
+  const uint64_t np = (n + 3) / 4, file_snps = (fsz >= 3 ? fsz - 3 : 0) / np;  // data.cpp:163-170
+  if (snp_begin > file_snps) snp_begin = file_snps;
+  if (snp_count == 0 || snp_begin + snp_count > file_snps) snp_count = file_snps - snp_begin;
+  if (snp_count == 0) FPB_FAIL((fpb_handle*)nullptr, "empty genotype matrix (N == 0 or nsnps == 0)");
+
+  fpb_handle* h = new fpb_handle();
+  int rc = [&]() -> int {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      FPB_FAIL(h, std::string("no usable CUDA device (flashpca_b200 has no CPU fallback): ") +
+                      cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) FPB_FAIL(h, "invalid CUDA device ordinal");
+    h->device = device;
+    FPB_CUDA(h, cudaSetDevice(device));
+    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    h->n = n;
+    h->nsnps = snp_count;
+    h->np = np;
+    h->pitch_s = (np + 63) / 64 * 64;
+    h->stand_method = stand_method;
+    const uint64_t slab = std::min(snps_per_slab, snp_count);
+    for (int i = 0; i < 2; i++) FPB_CUDA(h, cudaMalloc(&h->sbuf[i], h->pitch_s * slab));
+    FPB_CUDA(h, cudaMalloc(&h->d_ytmp, sizeof(double) * n));
+    std::vector<double> msd;
+    for (uint64_t off = 0; off < snp_count; off += slab) {
+      const uint64_t cnt = std::min(slab, snp_count - off);
+      const double* kid_msd = nullptr;
+      if (preloaded_meansd) {  // nsnps x 2 column-major -> the slab's cnt x 2
+        msd.resize(2 * cnt);
+        std::copy(preloaded_meansd + off, preloaded_meansd + off + cnt, msd.begin());
+        std::copy(preloaded_meansd + snp_count + off, preloaded_meansd + snp_count + off + cnt,
+                  msd.begin() + cnt);
+        kid_msd = msd.data();
+      }
+      fpb_handle* kid = nullptr;
+      if (fpb_create_from_file(&kid, bed_path, n, snp_begin + off, cnt, stand_method, kid_msd,
+                               device))
+        FPB_FAIL(h, g_err);
+      h->kids.push_back(kid);
+      h->kid_off.push_back(off);
+      h->kid_host.push_back(nullptr);
+      // the recoded genotypes leave HBM: pinned host memory is their home from now on
+      FPB_CUDA(h, cudaMallocHost(&h->kid_host.back(), kid->pitch_s * cnt));
+      FPB_CUDA(h, cudaMemcpy(h->kid_host.back(), kid->d_gs, kid->pitch_s * cnt,
+                             cudaMemcpyDeviceToHost));
+      cudaFree(kid->d_gs);
+      kid->d_gs = nullptr;
+      if (kid->use_imma && kid->use_tma)
+        for (int i = 0; i < 2; i++) {
+          if (make_tensor_map(kid, h->sbuf[i], kid->pitch_s, cnt, &kid->tm_s_alt[i]) ||
+              make_tensor_map(kid, h->sbuf[i], kid->pitch_s, cnt, &kid->tm_f_alt[i], fpb::kFRows))
+            FPB_FAIL(h, kid->err);
+        }
+      cudaStreamDestroy(kid->stream);
+      cudaStreamDestroy(kid->side);
+      kid->stream = h->stream;
+      kid->side = h->side;
+      kid->borrowed = true;
+      h->trace += kid->trace;  // slab order, like the block loop of svdwide.cpp:44-61
+      h->launches += kid->launches;
+      kid->launches = 0;
+    }
+    return 0;
+  }();
   if (rc) {
     g_err = h->err;
     fpb_destroy(h);
@@ -1260,6 +1444,24 @@ void fpb_destroy(fpb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->side) cudaStreamSynchronize(h->side);
+  if (h->copy) cudaStreamSynchronize(h->copy);
+  for (fpb_handle* kid : h->kids) {
+    if (kid->borrowed) {  // streams and the slab buffer belong to this handle
+      kid->stream = nullptr;
+      kid->side = nullptr;
+      kid->d_gs = nullptr;
+    }
+    fpb_destroy(kid);
+  }
+  for (uint8_t* p : h->kid_host)
+    if (p) cudaFreeHost(p);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(h->sbuf[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  cudaFree(h->d_ytmp);
+  if (h->copy) cudaStreamDestroy(h->copy);
   delete h->solver;
   for (int i = 0; i < 4; i++)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
@@ -1310,6 +1512,17 @@ uint64_t fpb_launch_count(const fpb_handle* h) { return h ? h->launches : 0; }
 int fpb_get_meansd(fpb_handle* h, double* out_meansd) {
   if (!h || !out_meansd) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->kids.empty()) {  // concatenate the slabs' (mean, sd) columns
+    std::vector<double> tmp;
+    for (size_t b = 0; b < h->kids.size(); b++) {
+      const uint64_t cnt = h->kids[b]->nsnps;
+      tmp.resize(2 * cnt);
+      if (fpb_get_meansd(h->kids[b], tmp.data())) FPB_FAIL(h, h->kids[b]->err);
+      std::copy(tmp.begin(), tmp.begin() + cnt, out_meansd + h->kid_off[b]);
+      std::copy(tmp.begin() + cnt, tmp.end(), out_meansd + h->nsnps + h->kid_off[b]);
+    }
+    return 0;
+  }
   FPB_CUDA(h, cudaMemcpyAsync(out_meansd, h->d_meansd, sizeof(double) * 2 * h->nsnps,
                               cudaMemcpyDeviceToHost, h->stream));
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1325,6 +1538,7 @@ int fpb_get_trace(fpb_handle* h, double* out_trace) {
 int fpb_get_bed(fpb_handle* h, unsigned char* out_payload) {
   if (!h || !out_payload) FPB_FAIL(h, "null argument");
   if (h->dense) FPB_FAIL(h, "fpb_get_bed: the handle holds a dense matrix, not a bed");
+  if (!h->kids.empty()) FPB_FAIL(h, "fpb_get_bed: not available in streaming mode");
   FPB_CUDA(h, cudaSetDevice(h->device));
   uint8_t* d_tmp = nullptr;
   uint64_t total = h->nsnps * h->np;
@@ -1561,7 +1775,7 @@ int fpb_time_perform_op(fpb_handle* h, const double* d_x, double* d_y, uint32_t 
     // one more op with events around each half, and around each contraction kernel
     for (int i = 0; i < 4; i++)
       if (!h->kev[i]) cudaEventCreate(&h->kev[i]);
-    h->time_gemv = h->use_imma;
+    h->time_gemv = h->use_imma && h->kids.empty();
     const bool fused = h->use_imma && h->use_fused && !h->dense;
     cudaEventRecord(e0, h->stream);
     if (fused) {
@@ -1603,8 +1817,26 @@ int fpb_fused_debug(fpb_handle* h, unsigned long long* out, uint64_t count) {
   return 0;
 }
 
+int fpb_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes) {
+  if (!free_bytes || !total_bytes) FPB_FAIL((fpb_handle*)nullptr, "null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    FPB_FAIL((fpb_handle*)nullptr,
+             std::string("no usable CUDA device (flashpca_b200 has no CPU fallback): ") +
+                 cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) FPB_FAIL((fpb_handle*)nullptr, "invalid CUDA device ordinal");
+  FPB_CUDA((fpb_handle*)nullptr, cudaSetDevice(device));
+  size_t fr = 0, tot = 0;
+  FPB_CUDA((fpb_handle*)nullptr, cudaMemGetInfo(&fr, &tot));
+  *free_bytes = fr;
+  *total_bytes = tot;
+  return 0;
+}
+
 unsigned fpb_path_info(const fpb_handle* h) {
   if (!h) return 0;
+  if (!h->kids.empty()) return FPB_PATH_STREAMING | fpb_path_info(h->kids[0]);
   return (h->dense ? FPB_PATH_DENSE : 0u) | (h->use_imma ? FPB_PATH_TENSOR : 0u) |
          (h->use_imma && h->use_tma ? FPB_PATH_TMA : 0u) |
          (h->use_imma && h->single_copy ? FPB_PATH_SINGLE_COPY : 0u) |

@@ -9,6 +9,9 @@
 // Errors surface as std::runtime_error, as upstream's Data I/O does
 // (data.cpp:160,188,287).
 #pragma once
+#include <cstdlib>
+#include <algorithm>
+#include <iostream>
 #include <stdexcept>
 #include <string>
 
@@ -79,10 +82,27 @@ class SVDWideOnline {
     const double* pre = dat.use_preloaded_maf ? dat.X_meansd.data() : nullptr;
     if (dat.use_preloaded_maf && dat.X_meansd.rows() != dat.nsnps)
       throw std::runtime_error("preloaded mean/sd table does not match the number of SNPs");
+    // A bed that fits in HBM is staged once and stays there.  One that does not is kept in pinned
+    // host memory and streamed slab by slab on every op -- the role upstream's --memory / block_size
+    // plays (flashpca.cpp:649-676), chosen here from the device's free memory.  FPB_STREAM_SLAB_SNPS
+    // forces the streaming mode with that many SNPs per slab.
+    uint64_t slab = 0;
+    if (const char* sv = getenv("FPB_STREAM_SLAB_SNPS")) slab = strtoull(sv, nullptr, 10);
+    if (!slab) {
+      uint64_t free_b = 0, total_b = 0;
+      if (fpb_device_memory(device, &free_b, &total_b))
+        throw std::runtime_error(fpb_last_error(nullptr));
+      const uint64_t np = ((uint64_t)dat.N + 3) / 4, bed = np * dat.nsnps;
+      if (bed + bed / 16 > free_b / 10 * 9) slab = std::max<uint64_t>(1, free_b / 4 / np);
+    }
     // the standardisation method is Data's, as in data.cpp:279-288
-    if (fpb_create_from_file(&h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps,
-                             dat.stand_method_x, pre, device))
-      throw std::runtime_error(fpb_last_error(nullptr));
+    const int rc = slab ? fpb_create_streaming(&h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps, slab,
+                                               dat.stand_method_x, pre, device)
+                        : fpb_create_from_file(&h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps,
+                                               dat.stand_method_x, pre, device);
+    if (rc) throw std::runtime_error(fpb_last_error(nullptr));
+    if (slab && verbose)
+      std::cout << "bed streamed from host memory, " << slab << " SNPs per slab" << std::endl;
     fpb_get_trace(h, &trace);
     if (!dat.use_preloaded_maf) {
       dat.X_meansd = Matrix(p, 2);

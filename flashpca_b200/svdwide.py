@@ -62,7 +62,7 @@ class SVDWideOnline:
                  verbose: bool = False, *, payload: np.ndarray | None = None,
                  n: int | None = None, nsnps: int | None = None, device: int = 0,
                  snp_begin: int = 0, snp_count: int = 0, meansd: np.ndarray | None = None,
-                 _handle=None):
+                 snps_per_slab: int = 0, _handle=None):
         self.lib = _lib.load()
         self.verbose = verbose
         self.block_size = block_size  # accepted for interface parity; HBM-resident, unused
@@ -84,6 +84,11 @@ class SVDWideOnline:
                 raise FpbError("packed genotype buffer too small")
             check(self.lib.fpb_create(ctypes.byref(self.h), payload.ctypes.data, n, nsnps,
                                       stand_method, msd, device))
+        elif snps_per_slab:
+            # out-of-HBM mode: genotypes in pinned host memory, streamed slab by slab per op
+            check(self.lib.fpb_create_streaming(ctypes.byref(self.h), dat.geno_filename.encode(),
+                                                dat.N, snp_begin, snp_count, snps_per_slab,
+                                                stand_method, msd, device))
         else:
             check(self.lib.fpb_create_from_file(ctypes.byref(self.h),
                                                 dat.geno_filename.encode(), dat.N, snp_begin,

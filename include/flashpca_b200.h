@@ -67,6 +67,19 @@ int fpb_create_from_file(fpb_handle **out, const char *bed_path, uint64_t n_indi
                          uint64_t snp_begin, uint64_t snp_count, int stand_method,
                          const double *preloaded_meansd, int device);
 
+/* fpb_create_streaming: out-of-HBM mode for beds larger than one GPU's memory
+ * (replaces the disk loop of Data::read_snp_block, data.cpp:215-335).
+ * The recoded 2-bit matrix is kept in pinned host memory in slabs of
+ * snps_per_slab SNP columns; every operator call streams the slabs through two
+ * device buffers (the copy of slab b+1 overlaps the kernels of slab b) and
+ * accumulates y = sum_b X_b X_b' x in slab order, the reference's block loop
+ * (svdwide.cpp:48-59).  Statistics and missing-genotype lists of every slab
+ * stay on the device.  All operator entry points, fpb_pca and the multi-GPU
+ * calls accept the handle; fpb_get_bed does not. */
+int fpb_create_streaming(fpb_handle **out, const char *bed_path, uint64_t n_individuals,
+                         uint64_t snp_begin, uint64_t snp_count, uint64_t snps_per_slab,
+                         int stand_method, const double *preloaded_meansd, int device);
+
 /* fpb_create_synthetic: generate the packed genotypes directly in HBM
  * (bench-only input path; counter-based integer hash, reproduced bit for bit
  * on the host by flashpca_b200/synth.py).  pop_of_individual: N bytes;
@@ -178,7 +191,12 @@ int fpb_time_perform_op(fpb_handle *h, const double *d_x, double *d_y, uint32_t 
 #define FPB_PATH_TMA 4u         /* TMA + mbarrier pipelines */
 #define FPB_PATH_SINGLE_COPY 8u /* both halves read the one SNP-major copy */
 #define FPB_PATH_FUSED 16u      /* perform_op reads HBM once (fused two-phase kernel) */
+#define FPB_PATH_STREAMING 32u  /* genotypes in pinned host memory, streamed per op */
 unsigned fpb_path_info(const fpb_handle *h);
+
+/* Free and total memory of a device, bytes (hosts use it to choose between
+ * fpb_create_from_file and fpb_create_streaming). */
+int fpb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 
 /* Debug: with FPB_FUSED_DEBUG=1 in the environment at staging, the fused kernel
  * records globaltimer stamps of its cross-CTA protocol for the first 256 slabs

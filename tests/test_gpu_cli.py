@@ -183,3 +183,23 @@ def test_flashpcar_entry_points(mode, stand, divisor, tmp_path):
         assert res["rownames"] == [a + ":" + b for a, b in zip(fid, iid)]
     else:
         assert res["rownames"] == []
+
+
+def test_cli_streaming_mode_matches_resident(cli, tmp_path):
+    """FPB_STREAM_SLAB_SNPS forces the out-of-HBM mode of the C++ front end (the
+    role of upstream's --memory block size): same output files."""
+    stem = FIXTURES["data_chr1"]
+    outs = {}
+    for tag, env in (("res", {}), ("str", {"FPB_STREAM_SLAB_SNPS": "200"})):
+        wd = tmp_path / tag
+        wd.mkdir()
+        e = dict(os.environ)
+        e.pop("FPB_STREAM_SLAB_SNPS", None)
+        e.update(env)
+        out = subprocess.run([cli, "--bfile", stem, "--ndim", "5", "--tol", "1e-8", "--precision",
+                              "15", "--notime", "-v"], cwd=wd, capture_output=True, text=True, env=e)
+        assert out.returncode == 0, out.stdout + out.stderr
+        if tag == "str":
+            assert "streamed from host memory" in out.stdout
+        outs[tag] = np.loadtxt(wd / "eigenvalues.txt")
+    assert np.abs(outs["str"] / outs["res"] - 1).max() < 1e-9

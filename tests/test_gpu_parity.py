@@ -623,3 +623,89 @@ def test_persistent_and_one_shot_grids_agree(native_lib, monkeypatch):
     orc = O.COracle(s.packed_bed(0, 64), s.n, 64)
     sub = s.create_operator(j0=0, j1=64)
     assert _relerr(sub.perform_op(x), orc.perform_op(x, 0)) <= OP_RTOL
+
+
+# ---------------------------------------------------------------------------
+# Out-of-HBM streaming mode (fpb_create_streaming): slabs of SNP columns in
+# pinned host memory, streamed through two device buffers on every op.
+# ---------------------------------------------------------------------------
+def _streaming_op(name, slab, **kw):
+    from flashpca_b200 import Data, SVDWideOnline
+    stem = FIXTURES[name]
+    d = Data()
+    d.read_pheno(stem + ".fam", 6)
+    d.geno_filename = stem + ".bed"
+    d.get_size()
+    d.prepare()
+    return d, SVDWideOnline(d, 0, 3, snps_per_slab=slab, **kw)
+
+
+@pytest.mark.parametrize("name,slab", [("data_chr1", 300), ("data_chr1", 1129), ("data_chr1", 1),
+                                       ("hapmap3", 5000)])
+def test_streaming_operator_family(native_lib, path, name, slab):
+    """Ragged last slab, one slab, one SNP per slab; both compute paths.  The slab
+    loop is upstream's block loop (svdwide.cpp:48-59): same sums, block order."""
+    from flashpca_b200 import _lib
+    if slab == 1 and name == "data_chr1":
+        slab = 97   # 1129 = 11 * 97 + 62 slabs would be slow to stage; keep a ragged small slab
+    _, payload, n, p = load_fixture(name)
+    d, op = _streaming_op(name, slab)
+    assert op.path_info() & _lib.PATH_STREAMING
+    orc = O.COracle(payload, n, p)
+    rng = np.random.default_rng(61)
+    x, v = rng.standard_normal(n), rng.standard_normal(p)
+    y_ref = orc.perform_op(x, slab)                       # the reference's block size = the slab
+    assert np.array_equal(op.meansd(), orc.meansd())
+    assert np.array_equal(d.X_meansd, orc.meansd())
+    assert abs(op.trace - orc.trace) <= 1e-12 * orc.trace
+    y = op.perform_op(x)
+    assert _relerr(y, y_ref) <= OP_RTOL
+    if path == "imma":                                    # (the generic path sums with atomics)
+        assert np.array_equal(op.perform_op(x), y)        # bit-reproducible
+    assert _relerr(op.crossprod(x), orc.crossprod(x)) <= OP_RTOL
+    assert _relerr(op.prod(v), orc.prod(v)) <= OP_RTOL
+    m = rng.standard_normal((n, 2))
+    assert _relerr(op.perform_op_mat(m), orc.perform_op(m, 0)) <= OP_RTOL
+    with pytest.raises(_lib.FpbError, match="streaming"):
+        op.bed_payload()
+    op.close()
+
+
+def test_streaming_pca_matches_resident(native_lib, monkeypatch):
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    _, payload, n, p = load_fixture("hapmap3")
+    _, op = _streaming_op("hapmap3", 4000)
+    got = op.pca(10, 21, 500, 1e-6)
+    res = _mk(payload, n, p).pca(10, 21, 500, 1e-6)
+    assert got["nconv"] == 10
+    assert np.abs(got["values"] / res["values"] - 1).max() < 1e-9
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, 10)
+    assert np.abs(got["values"] / p / ref["d"] - 1).max() < 1e-6
+
+
+def test_streaming_preloaded_meansd_and_shard(native_lib, path):
+    """Preloaded (mean, sd) are split per slab; a streamed SNP shard equals the
+    resident shard."""
+    from flashpca_b200 import Data, SVDWideOnline
+    _, payload, n, p = load_fixture("data_chr1")
+    base = O.COracle(payload, n, p)
+    base.perform_op(np.ones(n), 0)
+    maf = base.meansd()[:, 0] / 2.0
+    pre = np.asfortranarray(np.stack([2 * maf, 2 * maf * (1 - maf)], axis=1))
+    stem = FIXTURES["data_chr1"]
+    d = Data()
+    d.read_pheno(stem + ".fam", 6)
+    d.geno_filename = stem + ".bed"
+    d.get_size()
+    d.prepare()
+    x = np.random.default_rng(9).standard_normal(n)
+    op = SVDWideOnline(d, 0, 3, snps_per_slab=250, meansd=pre)
+    orc = O.COracle(payload, n, p, meansd=pre)
+    assert _relerr(op.perform_op(x), orc.perform_op(x, 0)) <= OP_RTOL
+    assert np.array_equal(op.meansd(), pre)
+    a = SVDWideOnline(d, 0, 3, snp_begin=200, snp_count=700, snps_per_slab=256)
+    b = SVDWideOnline(d, 0, 3, snp_begin=200, snp_count=700)
+    assert a.p == b.p == 700
+    assert _relerr(a.perform_op(x), b.perform_op(x)) <= 1e-13
+    assert np.array_equal(a.meansd(), b.meansd())
