@@ -372,6 +372,27 @@ def run_b200(a):
                  "note": "250 MB matrix: two HBM passes + 9 launches per op; launch-bound"}
         sop.close()
 
+    # the block variant (perform_op_mat, svdwide.cpp:71-118): two columns per pass over the matrix
+    block = None
+    if world == 1:
+        xb = torch.randn(2 * n, dtype=torch.float64, device="cuda")
+        yb = torch.empty_like(xb)
+        lstream = torch.cuda.ExternalStream(lib.fpb_stream(op.h))
+        _lib.check(lib.fpb_perform_op_multi_dev(op.h, xb.data_ptr(), 2, yb.data_ptr()), op.h)
+        _lib.check(lib.fpb_sync(op.h), op.h)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(lstream):
+            e0.record()
+            for _ in range(5):
+                _lib.check(lib.fpb_perform_op_multi_dev(op.h, xb.data_ptr(), 2, yb.data_ptr()), op.h)
+            e1.record()
+        _lib.check(lib.fpb_sync(op.h), op.h)
+        b_ms = e0.elapsed_time(e1) / 5
+        block = {"columns": 2, "ms_per_call": b_ms, "value_per_column": 2 * n * p / (b_ms * 1e-3),
+                 "unit": UNIT, "note": "fpb_perform_op_multi_dev, k = 2: both columns from one pass "
+                                       "over the packed matrix per half (k_imma_gemv_tma*_2v)"}
+        del xb, yb
+
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         snps = a.cpu_sample_snps or max(64, min(p, int(1e9 // n)))
@@ -410,6 +431,7 @@ def run_b200(a):
         "cpu_baseline": cpu,
         "solve": solve,
         "config_10k_x_100k": small,
+        "block_variant": block,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -148,6 +148,15 @@ struct fpb_handle {
   uint32_t* d_fsync = nullptr;             // watchdog error word
   unsigned long long* d_fdbg = nullptr;    // FPB_FUSED_DEBUG: time stamps of two CTAs
   bool fused_used = false;                 // an op ran through the fused kernel since the last check
+  // second set of per-vector scratch for the two-vector kernels (allocated on first use)
+  struct Scratch {
+    uint4* slices = nullptr;
+    double *part = nullptr, *a = nullptr, *corr = nullptr, *pmax = nullptr, *psum = nullptr;
+    double *mx = nullptr, *mc = nullptr;
+    fpb::VecScale* sc = nullptr;
+    uint32_t nparts = 0;
+  } L1;
+  size_t slice_bytes = 0, part_elems = 0, max_parts = 0;
   // out-of-HBM streaming (fpb_create_streaming): the parent owns SNP slabs ("kids": ordinary
   // handles whose genotypes live in pinned host memory), two device slab buffers and a copy stream
   std::vector<fpb_handle*> kids;
@@ -674,6 +683,12 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
     }
     if (h->single_copy) {
       if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_f, fpb::kFRows)) return 1;
+      FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma_2v,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fpb::kTmaSmemBytes));
+      FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma_t_2v,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fpb::kTmaSmemBytes));
       FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_imma_gemv_tma_tw,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        fpb::kTmaSmemBytes));
@@ -693,16 +708,18 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
   // the K-major slices of the single-copy second half need 8 bytes per SNP, padded to whole tiles
   uint64_t slice_bytes = std::max<uint64_t>(sizeof(uint4) * max_chunks * fpb::kChunkWords * 8,
                                             (uint64_t)(h->ttiles + 1) * fpb::kTmaTSliceBytes);
+  h->slice_bytes = slice_bytes;
   FPB_CUDA(h, cudaMalloc(&h->d_slices, slice_bytes));
-  FPB_CUDA(h, cudaMalloc(&h->d_part,
-                         sizeof(double) * h->part_stride *
-                             std::max(std::max(std::max(std::max(h->splits_s, h->splits_i),
-                                                        std::max(h->tsplits_s, h->tsplits_i)),
-                                               h->ttsplits),
-                                      std::max(std::max(h->psplits_s, h->psplits_t), h->wsplits))));
+  h->part_elems = h->part_stride *
+                  std::max(std::max(std::max(std::max(h->splits_s, h->splits_i),
+                                             std::max(h->tsplits_s, h->tsplits_i)),
+                                    h->ttsplits),
+                           std::max(std::max(h->psplits_s, h->psplits_t), h->wsplits));
+  FPB_CUDA(h, cudaMalloc(&h->d_part, sizeof(double) * h->part_elems));
   FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * h->nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * h->nsnps));
   const size_t max_parts = std::max<size_t>(kVecBlocks, (h->nsnps + 255) / 256);
+  h->max_parts = max_parts;
   FPB_CUDA(h, cudaMalloc(&h->d_pmax, sizeof(double) * max_parts));
   FPB_CUDA(h, cudaMalloc(&h->d_psum, sizeof(double) * max_parts));
   FPB_CUDA(h, cudaMalloc(&h->d_sc, sizeof(fpb::VecScale) * 2));
@@ -1007,6 +1024,123 @@ int check_fused(fpb_handle* h) {
     FPB_FAIL(h, "fused perform_op kernel: wait timed out (code " + std::to_string(code) + ")");
   }
   return 0;
+}
+
+// ------------------------------ two vectors per pass ------------------------
+// The block variants process their columns in pairs: per-vector small kernels run
+// once per lane (lane 1 = a second set of scratch buffers, swapped in around the
+// calls), the two contraction kernels read the packed matrix once for both.
+
+bool pair_capable(const fpb_handle* h) {
+  static const bool off = getenv("FPB_PAIR") && atoi(getenv("FPB_PAIR")) == 0;
+  return !off && h->kids.empty() && !h->dense && h->use_imma && h->use_tma && h->single_copy;
+}
+
+int ensure_lane1(fpb_handle* h) {
+  if (h->L1.slices) return 0;
+  FPB_CUDA(h, cudaMalloc(&h->L1.slices, h->slice_bytes));
+  FPB_CUDA(h, cudaMalloc(&h->L1.part, sizeof(double) * h->part_elems));
+  FPB_CUDA(h, cudaMalloc(&h->L1.a, sizeof(double) * h->nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->L1.corr, sizeof(double) * h->nsnps));
+  FPB_CUDA(h, cudaMalloc(&h->L1.pmax, sizeof(double) * h->max_parts));
+  FPB_CUDA(h, cudaMalloc(&h->L1.psum, sizeof(double) * h->max_parts));
+  FPB_CUDA(h, cudaMalloc(&h->L1.sc, sizeof(fpb::VecScale) * 2));
+  if (h->nmissing) {
+    FPB_CUDA(h, cudaMalloc(&h->L1.mx, sizeof(double) * h->nsnps * h->gtiles_s));
+    FPB_CUDA(h, cudaMalloc(&h->L1.mc, sizeof(double) * h->n * h->gtiles_i));
+  }
+  return 0;
+}
+void swap_lane(fpb_handle* h) {
+  std::swap(h->d_slices, h->L1.slices);
+  std::swap(h->d_part, h->L1.part);
+  std::swap(h->d_a, h->L1.a);
+  std::swap(h->d_corr, h->L1.corr);
+  std::swap(h->d_pmax, h->L1.pmax);
+  std::swap(h->d_psum, h->L1.psum);
+  std::swap(h->d_sc, h->L1.sc);
+  std::swap(h->d_mx, h->L1.mx);
+  std::swap(h->d_mc, h->L1.mc);
+  std::swap(h->nparts, h->L1.nparts);
+}
+
+// first halves of two vectors: t = X'x (d_t*, optional) and/or the inputs of the second half
+void imma_crossprod_pair(fpb_handle* h, const double* d_x0, const double* d_x1, double* d_t0,
+                         double* d_t1, bool second_half) {
+  const uint32_t nwq = h->nchunks_s * fpb::kChunkWords;
+  if (h->nmissing) fork_mark(h);
+  for (int l = 0; l < 2; l++) {
+    const double* d_x = l ? d_x1 : d_x0;
+    if (l) swap_lane(h);
+    if (h->nmissing) gather_launch(h, true, d_x);
+    vec_partials(h, d_x, h->n);
+    fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(
+        d_x, h->n, nwq, h->d_pmax, h->d_psum, h->nparts, h->d_sc + 0, h->d_slices);
+    h->launches++;
+    if (l) swap_lane(h);
+  }
+  const uint32_t rows = (uint32_t)h->nsnps;
+  dim3 grid((rows + fpb::kTmaRows - 1) / fpb::kTmaRows, h->tsplits_s);
+  fpb::k_imma_gemv_tma_2v<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
+                            h->stream>>>(h->tm_s, rows, h->d_slices, h->L1.slices, h->nstages_s,
+                                         h->sps_s, h->d_part, h->L1.part, h->part_stride);
+  h->launches++;
+  if (h->nmissing) join_gather(h);
+  const uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
+  for (int l = 0; l < 2; l++) {
+    if (l) swap_lane(h);
+    fpb::k_finalize_crossprod<<<gb, 256, 0, h->stream>>>(
+        h->d_part, h->tsplits_s, h->part_stride, (uint32_t)h->nsnps, h->d_sc + 0, h->d_scale,
+        h->nmissing ? h->d_mx : nullptr, h->gtiles_s, l ? d_t1 : d_t0,
+        second_half ? h->d_a : nullptr, h->d_corr, h->d_pmax, h->d_psum);
+    if (second_half) h->nparts = gb;
+    h->launches++;
+    if (l) swap_lane(h);
+  }
+}
+
+// second halves of two vectors from the a, corr and partials in the two lanes
+void imma_prod_tail_pair(fpb_handle* h, double* d_y0, double* d_y1) {
+  const uint32_t ngroups4 = h->ttiles * (fpb::kTmaRows / 4);
+  if (h->nmissing) fork_mark(h);
+  for (int l = 0; l < 2; l++) {
+    if (l) swap_lane(h);
+    if (h->nmissing) gather_launch(h, false, h->d_corr);
+    fpb::k_slice_vec_k<<<(ngroups4 + 127) / 128, 128, 0, h->stream>>>(
+        h->d_a, h->nsnps, ngroups4, h->d_pmax, h->d_psum, h->nparts, h->d_sc + 1,
+        reinterpret_cast<uint32_t*>(h->d_slices));
+    h->launches++;
+    if (l) swap_lane(h);
+  }
+  dim3 grid(h->nstages_s, h->ttsplits);
+  fpb::k_imma_gemv_tma_t_2v<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
+                              h->stream>>>(h->tm_s, (uint32_t)h->n,
+                                           reinterpret_cast<const uint32_t*>(h->d_slices),
+                                           reinterpret_cast<const uint32_t*>(h->L1.slices), h->ttiles,
+                                           h->ttps, h->d_part, h->L1.part, h->part_stride);
+  h->launches++;
+  if (h->nmissing) join_gather(h);
+  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
+  for (int l = 0; l < 2; l++) {
+    if (l) swap_lane(h);
+    fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, h->ttsplits, h->part_stride, h->n,
+                                                    h->d_sc + 1, h->nmissing ? h->d_mc : nullptr,
+                                                    h->gtiles_i, l ? d_y1 : d_y0);
+    h->launches++;
+    if (l) swap_lane(h);
+  }
+}
+
+void prod_inputs_pair(fpb_handle* h, const double* d_v0, const double* d_v1) {
+  const uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
+  for (int l = 0; l < 2; l++) {
+    if (l) swap_lane(h);
+    fpb::k_prod_inputs<<<gb, 256, 0, h->stream>>>(l ? d_v1 : d_v0, h->d_scale, (uint32_t)h->nsnps,
+                                                  h->d_a, h->d_corr, h->d_pmax, h->d_psum);
+    h->nparts = gb;
+    h->launches++;
+    if (l) swap_lane(h);
+  }
 }
 
 // in-memory matrix path (svdwide.cpp:4-12)
@@ -1484,6 +1618,15 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_sc);
   cudaFree(h->d_mx);
   cudaFree(h->d_mc);
+  cudaFree(h->L1.slices);
+  cudaFree(h->L1.part);
+  cudaFree(h->L1.a);
+  cudaFree(h->L1.corr);
+  cudaFree(h->L1.pmax);
+  cudaFree(h->L1.psum);
+  cudaFree(h->L1.sc);
+  cudaFree(h->L1.mx);
+  cudaFree(h->L1.mc);
   cudaFree(h->d_fpart);
   cudaFree(h->d_ybuf);
   cudaFree(h->d_arep);
@@ -1564,7 +1707,14 @@ int fpb_sync(fpb_handle* h) {
 int fpb_crossprod_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, double* d_y) {
   if (!h || !d_m || !d_y || k == 0) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
-  for (uint32_t c = 0; c < k; c++)
+  uint32_t c = 0;
+  if (k >= 2 && pair_capable(h)) {
+    if (ensure_lane1(h)) return 1;
+    for (; c + 1 < k; c += 2)
+      imma_crossprod_pair(h, d_m + (uint64_t)c * h->n, d_m + (uint64_t)(c + 1) * h->n,
+                          d_y + (uint64_t)c * h->nsnps, d_y + (uint64_t)(c + 1) * h->nsnps, false);
+  }
+  for (; c < k; c++)
     launch_crossprod(h, d_m + (uint64_t)c * h->n, d_y + (uint64_t)c * h->nsnps);
   return check_launch(h);
 }
@@ -1572,8 +1722,15 @@ int fpb_crossprod_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, double
 int fpb_prod_multi_dev(fpb_handle* h, const double* d_v, uint32_t k, double* d_y) {
   if (!h || !d_v || !d_y || k == 0) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
-  for (uint32_t c = 0; c < k; c++)
-    launch_prod(h, d_v + (uint64_t)c * h->nsnps, d_y + (uint64_t)c * h->n);
+  uint32_t c = 0;
+  if (k >= 2 && pair_capable(h)) {
+    if (ensure_lane1(h)) return 1;
+    for (; c + 1 < k; c += 2) {
+      prod_inputs_pair(h, d_v + (uint64_t)c * h->nsnps, d_v + (uint64_t)(c + 1) * h->nsnps);
+      imma_prod_tail_pair(h, d_y + (uint64_t)c * h->n, d_y + (uint64_t)(c + 1) * h->n);
+    }
+  }
+  for (; c < k; c++) launch_prod(h, d_v + (uint64_t)c * h->nsnps, d_y + (uint64_t)c * h->n);
   if (check_launch(h)) return 1;
   return allreduce(h, d_y, (size_t)h->n * k);
 }
@@ -1581,8 +1738,16 @@ int fpb_prod_multi_dev(fpb_handle* h, const double* d_v, uint32_t k, double* d_y
 int fpb_perform_op_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, double* d_y) {
   if (!h || !d_m || !d_y || k == 0) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
-  for (uint32_t c = 0; c < k; c++)
-    launch_perform_op(h, d_m + (uint64_t)c * h->n, d_y + (uint64_t)c * h->n);
+  uint32_t c = 0;
+  if (k >= 2 && pair_capable(h) && !h->use_fused) {
+    if (ensure_lane1(h)) return 1;
+    for (; c + 1 < k; c += 2) {
+      imma_crossprod_pair(h, d_m + (uint64_t)c * h->n, d_m + (uint64_t)(c + 1) * h->n, nullptr,
+                          nullptr, true);
+      imma_prod_tail_pair(h, d_y + (uint64_t)c * h->n, d_y + (uint64_t)(c + 1) * h->n);
+    }
+  }
+  for (; c < k; c++) launch_perform_op(h, d_m + (uint64_t)c * h->n, d_y + (uint64_t)c * h->n);
   if (check_launch(h)) return 1;
   return allreduce(h, d_y, (size_t)h->n * k);
 }

@@ -753,6 +753,267 @@ k_imma_gemv_tma_t(const __grid_constant__ TmaDesc tmap, uint32_t C /* output len
 }
 
 // ---------------------------------------------------------------------------
+// Two-vector forms (the block variants perform_op_mat / crossprod2 / prod3,
+// svdwide.cpp:71-118, 157-188, 312-343): one pass over the packed matrix serves
+// two input vectors.  The masked A fragments are built once and fed to two sets
+// of IMMAs (the digit slices of both vectors travel with every stage), so the
+// LOP3 decode and the HBM traffic are shared; the tensor pipe, at ~40 % for one
+// vector, has room for the second.
+// ---------------------------------------------------------------------------
+constexpr int kTma2Stages = 5;
+constexpr int kTma2StageBytes = kTmaTileBytes + 2 * kTmaSliceBytes;          // 40 KB
+static_assert(kTma2Stages * kTma2StageBytes + 1024 + 128 <= kTmaSmemBytes, "ring too large");
+
+__global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
+k_imma_gemv_tma_2v(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* __restrict__ S0,
+                   const uint4* __restrict__ S1, uint32_t nstages, uint32_t stages_per_split,
+                   double* __restrict__ out0, double* __restrict__ out1, uint64_t out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kTma2Stages * kTma2StageBytes;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t s_begin = blockIdx.y * stages_per_split;
+  const uint32_t s_end = min(nstages, s_begin + stages_per_split);
+  const uint32_t nst = s_end > s_begin ? s_end - s_begin : 0;
+  const uint32_t row0 = blockIdx.x * kTmaRows;
+  if (tid == 0) {
+    for (int i = 0; i < kTma2Stages; i++) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (kTma2Stages + i), kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == kTmaConsumerWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+      for (uint32_t it = 0; it < nst; it++) {
+        const uint32_t slot = it % kTma2Stages, round = it / kTma2Stages;
+        const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTma2Stages + slot);
+        if (round > 0) mbar_wait(empty, (round - 1) & 1);
+        const uint32_t dst = base + slot * kTma2StageBytes;
+        mbar_expect_tx(full, kTma2StageBytes);
+        tma_load_2d(dst, &tmap, (int)((s_begin + it) * kTmaStageCols), (int)row0, full, pol_stream);
+        const uint64_t so = (uint64_t)(s_begin + it) * (kTmaSliceBytes / 16);
+        bulk_load(dst + kTmaTileBytes, S0 + so, kTmaSliceBytes, full, pol_keep);
+        bulk_load(dst + kTmaTileBytes + kTmaSliceBytes, S1 + so, kTmaSliceBytes, full, pol_keep);
+      }
+    }
+    return;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  uint32_t roff[2][2];
+#pragma unroll
+  for (int t = 0; t < 2; t++)
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) roff[t][hf] = (uint32_t)(warp * 32 + t * 16 + hf * 8 + rho) * 128u;
+  const uint32_t rx = (uint32_t)(rho & 7);
+  int acc[2][2][2][4] = {};   // [vector][tile][chain][frag]
+  double dacc[2][2][4] = {};
+  for (uint32_t it = 0; it < nst; it++) {
+    const uint32_t slot = it % kTma2Stages, round = it / kTma2Stages;
+    mbar_wait(bars + 8 * slot, round & 1);
+    const uint32_t tile = base + slot * kTma2StageBytes;
+    const uint32_t sl = tile + kTmaTileBytes;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t chunk = ((uint32_t)(u * 4 + q) ^ rx) << 4;
+      uint4 w[2][2];
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++)
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(w[t][hf].x), "=r"(w[t][hf].y), "=r"(w[t][hf].z), "=r"(w[t][hf].w)
+                       : "r"(tile + roff[t][hf] + chunk));
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int wl = u * 16 + q * 4 + j;
+        uint4 bv[2];
+#pragma unroll
+        for (int v = 0; v < 2; v++)
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(bv[v].x), "=r"(bv[v].y), "=r"(bv[v].z), "=r"(bv[v].w)
+                       : "r"(sl + (uint32_t)v * kTmaSliceBytes + (uint32_t)slice_slot(wl, g) * 16u));
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const uint32_t xa = j == 0 ? w[t][0].x : j == 1 ? w[t][0].y : j == 2 ? w[t][0].z : w[t][0].w;
+          const uint32_t xb = j == 0 ? w[t][1].x : j == 1 ? w[t][1].y : j == 2 ? w[t][1].z : w[t][1].w;
+          const uint32_t a0 = xa & 0x03030303u, a1 = xb & 0x03030303u, a2 = xa & 0x0F0F0F0Fu,
+                         a3 = xb & 0x0F0F0F0Fu, c0 = xa & 0x3F3F3F3Fu, c1 = xb & 0x3F3F3F3Fu;
+#pragma unroll
+          for (int v = 0; v < 2; v++) {
+            mma_u8s8(acc[v][t][0], a0, a1, a2, a3, bv[v].x, bv[v].y);
+            mma_u8s8(acc[v][t][1], c0, c1, xa, xb, bv[v].z, bv[v].w);
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // see k_imma_gemv_tma
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8 * (kTma2Stages + slot));
+    if ((it % kTmaFlushStages) == kTmaFlushStages - 1) {
+#pragma unroll
+      for (int v = 0; v < 2; v++)
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            dacc[v][t][k] += (double)acc[v][t][0][k] + (double)acc[v][t][1][k];
+            acc[v][t][0][k] = 0;
+            acc[v][t][1][k] = 0;
+          }
+    }
+  }
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+#pragma unroll
+  for (int v = 0; v < 2; v++) {
+    double* o = (v == 0 ? out0 : out1) + (uint64_t)blockIdx.y * out_stride;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[v][t][k] += (double)acc[v][t][0][k] + (double)acc[v][t][1][k];
+      double ra = dacc[v][t][0] * w0 + dacc[v][t][1] * w1;
+      double rb = dacc[v][t][2] * w0 + dacc[v][t][3] * w1;
+      ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+      ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+      if (q == 0) {
+        const uint32_t r = row0 + warp * 32 + t * 16 + rho;
+        if (r < R) o[r] = ra;
+        if (r + 8 < R) o[r + 8] = rb;
+      }
+    }
+  }
+}
+
+constexpr int kTmaT2StageBytes = kTmaTileBytes + 2 * kTmaTSliceBytes;          // 36 KB
+static_assert(kTmaStages * kTmaT2StageBytes + 1024 + 128 <= kTmaSmemBytes, "ring too large");
+
+__global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
+k_imma_gemv_tma_t_2v(const __grid_constant__ TmaDesc tmap, uint32_t C, const uint32_t* __restrict__ S0,
+                     const uint32_t* __restrict__ S1, uint32_t ntiles, uint32_t tiles_per_split,
+                     double* __restrict__ out0, double* __restrict__ out1, uint64_t out_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kTmaStages * kTmaT2StageBytes;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t t_begin = blockIdx.y * tiles_per_split;
+  const uint32_t t_end = min(ntiles, t_begin + tiles_per_split);
+  const uint32_t nst = t_end > t_begin ? t_end - t_begin : 0;
+  const uint32_t xbyte0 = blockIdx.x * kTmaStageCols;
+  if (tid == 0) {
+    for (int i = 0; i < kTmaStages; i++) {
+      mbar_init(bars + 8 * i, 1);
+      mbar_init(bars + 8 * (kTmaStages + i), kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == kTmaConsumerWarps) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+      for (uint32_t it = 0; it < nst; it++) {
+        const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+        const uint32_t full = bars + 8 * slot, empty = bars + 8 * (kTmaStages + slot);
+        if (round > 0) mbar_wait(empty, (round - 1) & 1);
+        const uint32_t dst = base + slot * kTmaT2StageBytes;
+        mbar_expect_tx(full, kTmaT2StageBytes);
+        tma_load_2d(dst, &tmap, (int)xbyte0, (int)((t_begin + it) * kTmaRows), full, pol_stream);
+        const uint64_t so = (uint64_t)(t_begin + it) * (kTmaTSliceBytes / 4);
+        bulk_load(dst + kTmaTileBytes, S0 + so, kTmaTSliceBytes, full, pol_keep);
+        bulk_load(dst + kTmaTileBytes + kTmaTSliceBytes, S1 + so, kTmaTSliceBytes, full, pol_keep);
+      }
+    }
+    return;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  int acc[2][4][4] = {};       // [vector][field (cumulative)][frag]
+  double dacc[2][4][4] = {};
+  for (uint32_t it = 0; it < nst; it++) {
+    const uint32_t slot = it % kTmaStages, round = it / kTmaStages;
+    mbar_wait(bars + 8 * slot, round & 1);
+    const uint32_t tile = base + slot * kTmaT2StageBytes;
+    const uint32_t sl = tile + kTmaTileBytes;
+#pragma unroll
+    for (int ks = 0; ks < kTmaRows / 32; ks++) {
+      const uint32_t row = (uint32_t)(ks * 32 + lane);
+      const uint32_t addr = tile + row * 128u + ((((uint32_t)warp) ^ (row & 7u)) << 4);
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                   : "r"(addr));
+      const uint32_t m00 = a0 & 0x03030303u, m01 = a1 & 0x03030303u, m02 = a2 & 0x03030303u,
+                     m03 = a3 & 0x03030303u, m10 = a0 & 0x0F0F0F0Fu, m11 = a1 & 0x0F0F0F0Fu,
+                     m12 = a2 & 0x0F0F0F0Fu, m13 = a3 & 0x0F0F0F0Fu, m20 = a0 & 0x3F3F3F3Fu,
+                     m21 = a1 & 0x3F3F3F3Fu, m22 = a2 & 0x3F3F3F3Fu, m23 = a3 & 0x3F3F3F3Fu;
+#pragma unroll
+      for (int v = 0; v < 2; v++) {
+        uint32_t b0, b1;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
+                     : "=r"(b0), "=r"(b1)
+                     : "r"(sl + (uint32_t)v * kTmaTSliceBytes + (uint32_t)(((ks * 8 + g) * 4 + q) * 8)));
+        mma_u8s8(acc[v][0], m00, m01, m02, m03, b0, b1);
+        mma_u8s8(acc[v][1], m10, m11, m12, m13, b0, b1);
+        mma_u8s8(acc[v][2], m20, m21, m22, m23, b0, b1);
+        mma_u8s8(acc[v][3], a0, a1, a2, a3, b0, b1);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // see k_imma_gemv_tma
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8 * (kTmaStages + slot));
+    if ((it % kTmaFlushStages) == kTmaFlushStages - 1) {
+#pragma unroll
+      for (int v = 0; v < 2; v++)
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            dacc[v][f][k] += (double)acc[v][f][k];
+            acc[v][f][k] = 0;
+          }
+    }
+  }
+  const double w0 = ldexp(1.0, 14 * q), w1 = ldexp(1.0, 14 * q + 7);
+  const uint64_t byte_a = (uint64_t)xbyte0 + warp * 16 + g;
+#pragma unroll
+  for (int v = 0; v < 2; v++) {
+    double* o = (v == 0 ? out0 : out1) + (uint64_t)blockIdx.y * out_stride;
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[v][f][k] += (double)acc[v][f][k];
+#pragma unroll
+    for (int f = 3; f > 0; f--)
+#pragma unroll
+      for (int k = 0; k < 4; k++) dacc[v][f][k] -= dacc[v][f - 1][k];
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const double sf = ldexp(1.0, -2 * f);
+      double ra = (dacc[v][f][0] * w0 + dacc[v][f][1] * w1) * sf;
+      double rb = (dacc[v][f][2] * w0 + dacc[v][f][3] * w1) * sf;
+      ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+      ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+      if (q == 0) {
+        const uint64_t ia = byte_a * 4 + f, ib = (byte_a + 8) * 4 + f;
+        if (ia < C) o[ia] = ra;
+        if (ib < C) o[ib] = rb;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Second half, wide-stripe form.  A CTA owns a 256-byte column stripe (1024
 // individuals): each stage holds two [128 rows x 128 B] boxes that are adjacent
 // in memory, so every SNP row is read in 256-byte runs (k_imma_gemv_tma_t reads
