@@ -168,6 +168,9 @@ struct fpb_handle {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   double* d_ytmp = nullptr;
   bool borrowed = false;                   // kid: streams and d_gs belong to the parent
+  // pinned bounce buffers for large device -> pageable-host downloads (fpb_pca eigenvectors)
+  unsigned char* h_bounce[2] = {nullptr, nullptr};
+  cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
   // host-pointer API staging (grown on demand)
   double* d_in = nullptr;
   double* d_out = nullptr;
@@ -1212,6 +1215,39 @@ int allreduce(fpb_handle* h, double* d_buf, size_t count) {
   return 0;
 }
 
+// Device -> pageable host copy through two pinned 16 MiB bounce buffers: the DMA of chunk c+1
+// overlaps the host memcpy of chunk c (a plain cudaMemcpy to pageable memory runs at ~4 GB/s,
+// 20 ms for the 80 MB of eigenvectors at N = 500k, k = 20).
+int download_pageable(fpb_handle* h, void* dst, const void* d_src, size_t bytes) {
+  constexpr size_t kChunk = 16u << 20;
+  if (bytes <= (1u << 20)) {
+    FPB_CUDA(h, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  for (int i = 0; i < 2; i++)
+    if (!h->h_bounce[i]) {
+      FPB_CUDA(h, cudaMallocHost(&h->h_bounce[i], kChunk));
+      FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_bounce[i], cudaEventDisableTiming));
+    }
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  auto issue = [&](size_t c) {
+    const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+    cudaMemcpyAsync(h->h_bounce[c & 1], (const char*)d_src + off, len, cudaMemcpyDeviceToHost,
+                    h->stream);
+    cudaEventRecord(h->ev_bounce[c & 1], h->stream);
+  };
+  issue(0);
+  for (size_t c = 0; c < nchunks; c++) {
+    FPB_CUDA(h, cudaEventSynchronize(h->ev_bounce[c & 1]));
+    if (c + 1 < nchunks) issue(c + 1);
+    const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+    memcpy((char*)dst + off, h->h_bounce[c & 1], len);
+  }
+  FPB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
 int check_launch(fpb_handle* h) {
   FPB_CUDA(h, cudaGetLastError());
   return 0;
@@ -1627,6 +1663,10 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->L1.sc);
   cudaFree(h->L1.mx);
   cudaFree(h->L1.mc);
+  for (int i = 0; i < 2; i++) {
+    if (h->h_bounce[i]) cudaFreeHost(h->h_bounce[i]);
+    if (h->ev_bounce[i]) cudaEventDestroy(h->ev_bounce[i]);
+  }
   cudaFree(h->d_fpart);
   cudaFree(h->d_ybuf);
   cudaFree(h->d_arep);
@@ -1893,9 +1933,9 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
     if (ensure_staging(h, 0, (size_t)h->n * nev)) return 1;
     solver.eigenvectors(h->d_out);
     t2 = now();
-    FPB_CUDA(h, cudaMemcpyAsync(evecs_out, h->d_out, sizeof(double) * h->n * nev,
-                                cudaMemcpyDeviceToHost, h->stream));
     FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+    t2 = now();
+    if (download_pageable(h, evecs_out, h->d_out, sizeof(double) * h->n * nev)) return 1;
     t3 = now();
   }
   h->pca_phase_s[0] = secs(t0, t1);
