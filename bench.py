@@ -152,7 +152,9 @@ def run_reference(a):
     snps = a.cpu_sample_snps or max(64, min(a.p, int(2.5e8 // a.n)))
     spec = SynthSpec(a.n, a.p)
     payload = spec.packed_bed(0, snps)
-    val, ms, threads, bs = cpu_port_run(a, payload, a.n, snps, a.steps, a.warmup)
+    # all host threads, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    val, ms, threads, bs = cpu_port_run(a, payload, a.n, snps, a.steps, a.warmup, threads=ncpu)
     sample = ("first %d of %d SNP columns x %d individuals per step (block_size %d from the "
               "--memory 2048 formula), bed bytes served from RAM" % (snps, a.p, a.n, bs))
     line = {
@@ -399,7 +401,9 @@ def run_b200(a):
         sub = spec.create_operator(device=local, j0=0, j1=snps)
         payload = sub.bed_payload()
         sub.close()
-        val, cms, threads, bs = cpu_port_run(a, payload, n, snps, steps=3, warmup=1)
+        ncpu = (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity")
+                else (os.cpu_count() or 1))
+        val, cms, threads, bs = cpu_port_run(a, payload, n, snps, steps=3, warmup=1, threads=ncpu)
         # BASELINE.md variant A: the reference is single-threaded in practice
         s1 = max(64, snps // 8)
         val1, _, _, _ = cpu_port_run(a, payload[: s1 * ((n + 3) // 4)], n, s1, steps=1, warmup=1,

@@ -709,3 +709,36 @@ def test_streaming_preloaded_meansd_and_shard(native_lib, path):
     assert a.p == b.p == 700
     assert _relerr(a.perform_op(x), b.perform_op(x)) <= 1e-13
     assert np.array_equal(a.meansd(), b.meansd())
+
+
+def test_two_vector_kernels_match_single_vector_path(native_lib, monkeypatch):
+    """The block variants take their columns two at a time (k_imma_gemv_tma_2v /
+    _t_2v, odd column counts leave one for the single-vector kernels); FPB_PAIR=0
+    loops over columns.  Same integer sums: results agree to the FP64 recombination."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    monkeypatch.delenv("FPB_GEMV", raising=False)
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(40003, 2501, seed=11, missing_rate=0.003)
+    rng = np.random.default_rng(5)
+    m = rng.standard_normal((s.n, 3))
+    v = rng.standard_normal((s.p, 5))
+    m[:, 1] *= 1e-40                      # very different scales per column: one step per lane
+    op = s.create_operator()
+    y, t, z = op.perform_op_mat(m), op.crossprod2(m), op.prod3(v)
+    assert np.array_equal(op.perform_op_mat(m), y)          # bit-reproducible
+    for j in range(3):
+        assert _relerr(y[:, j], op.perform_op(m[:, j])) <= 1e-13
+        assert _relerr(t[:, j], op.crossprod(m[:, j])) <= 1e-13
+    for j in range(5):
+        assert _relerr(z[:, j], op.prod(v[:, j])) <= 1e-13
+    sub = s.create_operator(j0=0, j1=64)
+    orc = O.COracle(s.packed_bed(0, 64), s.n, 64)
+    assert _relerr(sub.perform_op_mat(m), orc.perform_op(m, 0)) <= OP_RTOL
+
+
+def test_device_memory_query(native_lib):
+    import ctypes
+    fr, tot = ctypes.c_uint64(), ctypes.c_uint64()
+    assert native_lib.fpb_device_memory(0, ctypes.byref(fr), ctypes.byref(tot)) == 0
+    assert 0 < fr.value <= tot.value and tot.value > (8 << 30)
+    assert native_lib.fpb_device_memory(99, ctypes.byref(fr), ctypes.byref(tot)) != 0
