@@ -11,6 +11,10 @@
 // when the missing rate is <= 3 %) and the generic FP64 path (fpb_kernels.cuh).
 // FPB_PATH=generic|imma in the environment forces one (tests exercise both).
 // No CPU fallback exists: if CUDA is unusable every entry point fails.
+// Host-side pieces with a life of their own are textual includes of this translation unit:
+//   fpb_host_fused_setup.inl / fpb_host_fused.inl   fused single-pass kernel (setup, launch, errors)
+//   fpb_host_pairs.inl                              two vectors per pass (block variants)
+//   fpb_host_streaming.inl / _create.inl            out-of-HBM streaming mode
 #include "../../include/flashpca_b200.h"
 
 #include <cuda.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time
@@ -483,49 +487,7 @@ int make_tensor_map(fpb_handle* h, const uint8_t* base, uint64_t pitch, uint64_t
   return 0;
 }
 
-// Fused single-pass perform_op (fpb_fused.cuh): one persistent CTA per SM owns
-// <= kFSpc column stripes.  Opt-in (FPB_FUSED=1): it reads HBM once per op (ncu:
-// 13.2 GB vs 25.1 GB) but on B200 the two halves do not overlap on an SM -- the
-// kernel is bound by instruction issue (mma.sync + LOP3 decode), 4.2 ms against
-// 3.7 ms for the two HBM-bound kernels (profiles/r01_fused_*).
-int setup_fused(fpb_handle* h) {
-  h->f_nstripes = (uint32_t)((h->pitch_s + 127) / 128);
-  h->f_grid = std::min<uint32_t>((uint32_t)h->sm_count, h->f_nstripes);
-  const uint32_t spc = (h->f_nstripes + h->f_grid - 1) / h->f_grid;
-  const bool feasible = spc <= (uint32_t)fpb::kFSpc;
-  bool want = false;
-  if (const char* fv = getenv("FPB_FUSED")) want = feasible && atoi(fv) != 0;
-  if (want) {
-    int coop = 0;
-    FPB_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
-    if (!coop) want = false;
-  }
-  h->use_fused = want;
-  if (!want) return 0;
-  h->f_nslabs = (uint32_t)((h->nsnps + fpb::kFRows - 1) / fpb::kFRows);
-  h->f_gpad = (fpb::kFP1Groups * h->f_grid + 31) / 32 * 32;
-  if (const char* wv = getenv("FPB_FUSED_WINDOW"))
-    h->f_window = (uint32_t)std::min(std::max(atoi(wv), 2), fpb::kFASlots);  // >= 2: lagged slot release
-  if (const char* pv = getenv("FPB_FUSED_POL1")) h->f_pol1 = (uint32_t)atoi(pv);
-  if (const char* pv = getenv("FPB_FUSED_POL2")) h->f_pol2 = (uint32_t)atoi(pv);
-  if (const char* pv = getenv("FPB_FUSED_PREFETCH")) h->f_prefetch = (uint32_t)std::max(0, atoi(pv));
-  FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_fused_op, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fpb::kFSmemBytes));
-  const size_t part_bytes = sizeof(double) * (size_t)fpb::kFASlots * fpb::kFRows * h->f_gpad;
-  FPB_CUDA(h, cudaMalloc(&h->d_fpart, part_bytes));
-  FPB_CUDA(h, cudaMemsetAsync(h->d_fpart, 0xFF, part_bytes, h->stream));  // all-ones = free
-  FPB_CUDA(h, cudaMalloc(&h->d_ybuf, sizeof(double) * h->n));
-  h->f_rep_stride = (uint64_t)h->f_nslabs * fpb::kFRows;
-  FPB_CUDA(h, cudaMalloc(&h->d_arep, sizeof(double) * fpb::kFReplicas * h->f_rep_stride));
-  FPB_CUDA(h, cudaMalloc(&h->d_fsync, sizeof(uint32_t)));
-  FPB_CUDA(h, cudaMemsetAsync(h->d_fsync, 0, sizeof(uint32_t), h->stream));
-  if (getenv("FPB_FUSED_DEBUG")) {
-    const size_t db = sizeof(unsigned long long) * 2 * fpb::kFDbgSlabs * fpb::kFDbgEvents;
-    FPB_CUDA(h, cudaMalloc(&h->d_fdbg, db));
-    FPB_CUDA(h, cudaMemsetAsync(h->d_fdbg, 0, db, h->stream));
-  }
-  return 0;
-}
+#include "fpb_host_fused_setup.inl"
 
 // raw bed bytes are in d_gs (pitch_s): recode, statistics (data.cpp:257-322),
 // trace, and -- when the missing rate allows -- the tensor path's second copy
@@ -943,208 +905,9 @@ void imma_prod_tail(fpb_handle* h, double* d_y) {
   h->launches++;
 }
 
-// y = X X' x in one pass over the packed matrix (fpb_fused.cuh).  The missing-genotype
-// sums of the first half only depend on x and run before the fused kernel; the
-// second gather needs every corr_j and runs after it.
-void fused_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
-  if (h->nmissing) {
-    fork_mark(h);
-    gather_launch(h, true, d_x);
-  }
-  vec_partials(h, d_x, h->n);
-  const uint32_t nwq = h->nchunks_s * fpb::kChunkWords;
-  fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(
-      d_x, h->n, nwq, h->d_pmax, h->d_psum, h->nparts, h->d_sc + 0, h->d_slices);
-  cudaMemsetAsync(h->d_arep, 0xFF, sizeof(double) * fpb::kFReplicas * h->f_rep_stride,
-                  h->stream);  // all-ones = not written
-  if (h->nmissing) join_gather(h);
-  fpb::FusedArgs a;
-  a.n = (uint32_t)h->n;
-  a.nsnps = (uint32_t)h->nsnps;
-  a.nslabs = h->f_nslabs;
-  a.nstripes = h->f_nstripes;
-  a.window = h->f_window;
-  a.gpad = h->f_gpad;
-  a.mx_tiles = h->nmissing ? h->gtiles_s : 0;
-  a.pol1 = h->f_pol1;
-  a.pol2 = h->f_pol2;
-  a.prefetch = h->f_prefetch;
-  {
-    static const char* dm = getenv("FPB_FUSED_DBGMODE");
-    a.dbg_mode = dm ? (uint32_t)atoi(dm) : 0u;
-  }
-  a.xslices = h->d_slices;
-  a.sc_x = h->d_sc + 0;
-  a.scale = h->d_scale;
-  a.mxv = h->nmissing ? h->d_mx : nullptr;
-  a.part = h->d_fpart;
-  a.a_out = h->d_a;
-  a.a_rep = h->d_arep;
-  a.rep_stride = h->f_rep_stride;
-  a.corr_out = h->d_corr;
-  a.ybuf = h->d_ybuf;
-  a.f_out = h->d_part;
-  a.err = h->d_fsync;
-  a.dbg = h->d_fdbg;
-  void* params[] = {(void*)&h->tm_f, (void*)&a};
-  if (h->time_gemv) cudaEventRecord(h->kev[0], h->stream);
-  cudaLaunchCooperativeKernel((const void*)fpb::k_fused_op, dim3(h->f_grid), dim3(fpb::kFThreads),
-                              params, (size_t)fpb::kFSmemBytes, h->stream);
-  if (h->time_gemv) cudaEventRecord(h->kev[1], h->stream);
-  h->fused_used = true;
-  if (h->nmissing) {
-    fork_mark(h);
-    gather_launch(h, false, h->d_corr);
-  }
-  fpb::k_fused_sum_b<<<1, 1024, 0, h->stream>>>(h->d_a, h->d_scale, (uint32_t)h->nsnps,
-                                                 h->d_sc + 1);
-  if (h->nmissing) join_gather(h);
-  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
-  fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, 1, h->part_stride, h->n, h->d_sc + 1,
-                                                  h->nmissing ? h->d_mc : nullptr, h->gtiles_i,
-                                                  d_y);
-  h->launches += 4;  // slicing, fused op, Sb, finalize (gathers and partials count themselves)
-}
+#include "fpb_host_fused.inl"
 
-// The fused kernel reports a timed-out wait (a protocol failure) through a device
-// word instead of hanging; surfaced at the API's synchronisation points.
-int check_fused(fpb_handle* h) {
-  for (fpb_handle* kid : h->kids)
-    if (check_fused(kid)) {
-      h->err = kid->err;
-      return 1;
-    }
-  if (!h->fused_used) return 0;
-  h->fused_used = false;
-  uint32_t code = 0;
-  uint32_t* d_err = h->d_fsync;
-  FPB_CUDA(h, cudaMemcpyAsync(&code, d_err, sizeof(code), cudaMemcpyDeviceToHost, h->stream));
-  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (code) {
-    cudaMemsetAsync(d_err, 0, sizeof(code), h->stream);
-    cudaMemsetAsync(h->d_fpart, 0xFF,
-                    sizeof(double) * (size_t)fpb::kFASlots * fpb::kFRows * h->f_gpad, h->stream);
-    FPB_FAIL(h, "fused perform_op kernel: wait timed out (code " + std::to_string(code) + ")");
-  }
-  return 0;
-}
-
-// ------------------------------ two vectors per pass ------------------------
-// The block variants process their columns in pairs: per-vector small kernels run
-// once per lane (lane 1 = a second set of scratch buffers, swapped in around the
-// calls), the two contraction kernels read the packed matrix once for both.
-
-bool pair_capable(const fpb_handle* h) {
-  static const bool off = getenv("FPB_PAIR") && atoi(getenv("FPB_PAIR")) == 0;
-  return !off && h->kids.empty() && !h->dense && h->use_imma && h->use_tma && h->single_copy;
-}
-
-int ensure_lane1(fpb_handle* h) {
-  if (h->L1.slices) return 0;
-  FPB_CUDA(h, cudaMalloc(&h->L1.slices, h->slice_bytes));
-  FPB_CUDA(h, cudaMalloc(&h->L1.part, sizeof(double) * h->part_elems));
-  FPB_CUDA(h, cudaMalloc(&h->L1.a, sizeof(double) * h->nsnps));
-  FPB_CUDA(h, cudaMalloc(&h->L1.corr, sizeof(double) * h->nsnps));
-  FPB_CUDA(h, cudaMalloc(&h->L1.pmax, sizeof(double) * h->max_parts));
-  FPB_CUDA(h, cudaMalloc(&h->L1.psum, sizeof(double) * h->max_parts));
-  FPB_CUDA(h, cudaMalloc(&h->L1.sc, sizeof(fpb::VecScale) * 2));
-  if (h->nmissing) {
-    FPB_CUDA(h, cudaMalloc(&h->L1.mx, sizeof(double) * h->nsnps * h->gtiles_s));
-    FPB_CUDA(h, cudaMalloc(&h->L1.mc, sizeof(double) * h->n * h->gtiles_i));
-  }
-  return 0;
-}
-void swap_lane(fpb_handle* h) {
-  std::swap(h->d_slices, h->L1.slices);
-  std::swap(h->d_part, h->L1.part);
-  std::swap(h->d_a, h->L1.a);
-  std::swap(h->d_corr, h->L1.corr);
-  std::swap(h->d_pmax, h->L1.pmax);
-  std::swap(h->d_psum, h->L1.psum);
-  std::swap(h->d_sc, h->L1.sc);
-  std::swap(h->d_mx, h->L1.mx);
-  std::swap(h->d_mc, h->L1.mc);
-  std::swap(h->nparts, h->L1.nparts);
-}
-
-// first halves of two vectors: t = X'x (d_t*, optional) and/or the inputs of the second half
-void imma_crossprod_pair(fpb_handle* h, const double* d_x0, const double* d_x1, double* d_t0,
-                         double* d_t1, bool second_half) {
-  const uint32_t nwq = h->nchunks_s * fpb::kChunkWords;
-  if (h->nmissing) fork_mark(h);
-  for (int l = 0; l < 2; l++) {
-    const double* d_x = l ? d_x1 : d_x0;
-    if (l) swap_lane(h);
-    if (h->nmissing) gather_launch(h, true, d_x);
-    vec_partials(h, d_x, h->n);
-    fpb::k_slice_vec<<<(nwq + 127) / 128, 128, 0, h->stream>>>(
-        d_x, h->n, nwq, h->d_pmax, h->d_psum, h->nparts, h->d_sc + 0, h->d_slices);
-    h->launches++;
-    if (l) swap_lane(h);
-  }
-  const uint32_t rows = (uint32_t)h->nsnps;
-  dim3 grid((rows + fpb::kTmaRows - 1) / fpb::kTmaRows, h->tsplits_s);
-  fpb::k_imma_gemv_tma_2v<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
-                            h->stream>>>(h->tm_s, rows, h->d_slices, h->L1.slices, h->nstages_s,
-                                         h->sps_s, h->d_part, h->L1.part, h->part_stride);
-  h->launches++;
-  if (h->nmissing) join_gather(h);
-  const uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
-  for (int l = 0; l < 2; l++) {
-    if (l) swap_lane(h);
-    fpb::k_finalize_crossprod<<<gb, 256, 0, h->stream>>>(
-        h->d_part, h->tsplits_s, h->part_stride, (uint32_t)h->nsnps, h->d_sc + 0, h->d_scale,
-        h->nmissing ? h->d_mx : nullptr, h->gtiles_s, l ? d_t1 : d_t0,
-        second_half ? h->d_a : nullptr, h->d_corr, h->d_pmax, h->d_psum);
-    if (second_half) h->nparts = gb;
-    h->launches++;
-    if (l) swap_lane(h);
-  }
-}
-
-// second halves of two vectors from the a, corr and partials in the two lanes
-void imma_prod_tail_pair(fpb_handle* h, double* d_y0, double* d_y1) {
-  const uint32_t ngroups4 = h->ttiles * (fpb::kTmaRows / 4);
-  if (h->nmissing) fork_mark(h);
-  for (int l = 0; l < 2; l++) {
-    if (l) swap_lane(h);
-    if (h->nmissing) gather_launch(h, false, h->d_corr);
-    fpb::k_slice_vec_k<<<(ngroups4 + 127) / 128, 128, 0, h->stream>>>(
-        h->d_a, h->nsnps, ngroups4, h->d_pmax, h->d_psum, h->nparts, h->d_sc + 1,
-        reinterpret_cast<uint32_t*>(h->d_slices));
-    h->launches++;
-    if (l) swap_lane(h);
-  }
-  dim3 grid(h->nstages_s, h->ttsplits);
-  fpb::k_imma_gemv_tma_t_2v<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes,
-                              h->stream>>>(h->tm_s, (uint32_t)h->n,
-                                           reinterpret_cast<const uint32_t*>(h->d_slices),
-                                           reinterpret_cast<const uint32_t*>(h->L1.slices), h->ttiles,
-                                           h->ttps, h->d_part, h->L1.part, h->part_stride);
-  h->launches++;
-  if (h->nmissing) join_gather(h);
-  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
-  for (int l = 0; l < 2; l++) {
-    if (l) swap_lane(h);
-    fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, h->ttsplits, h->part_stride, h->n,
-                                                    h->d_sc + 1, h->nmissing ? h->d_mc : nullptr,
-                                                    h->gtiles_i, l ? d_y1 : d_y0);
-    h->launches++;
-    if (l) swap_lane(h);
-  }
-}
-
-void prod_inputs_pair(fpb_handle* h, const double* d_v0, const double* d_v1) {
-  const uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
-  for (int l = 0; l < 2; l++) {
-    if (l) swap_lane(h);
-    fpb::k_prod_inputs<<<gb, 256, 0, h->stream>>>(l ? d_v1 : d_v0, h->d_scale, (uint32_t)h->nsnps,
-                                                  h->d_a, h->d_corr, h->d_pmax, h->d_psum);
-    h->nparts = gb;
-    h->launches++;
-    if (l) swap_lane(h);
-  }
-}
+#include "fpb_host_pairs.inl"
 
 // in-memory matrix path (svdwide.cpp:4-12)
 void dense_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
@@ -1254,66 +1017,7 @@ int check_launch(fpb_handle* h) {
 }
 
 
-// ------------------------------ out-of-HBM streaming -----------------------
-// y = sum_b X_b X_b' x over SNP slabs, the reference's own block loop (svdwide.cpp:48-59,
-// Data::read_snp_block per block) with the disk re-read replaced by a pinned-host -> HBM
-// copy that overlaps the previous slab's kernels.
-
-__global__ void k_axpy1(double* __restrict__ y, const double* __restrict__ t, uint64_t n) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < n) y[i] += t[i];
-}
-
-// make slab b resident in buffer b & 1 (copy stream), order the compute stream behind it
-void stream_in(fpb_handle* h, size_t b) {
-  const int i = (int)(b & 1);
-  fpb_handle* kid = h->kids[b];
-  cudaStreamWaitEvent(h->copy, h->ev_done[i], 0);  // kernels of slab b - 2 are done with the buffer
-  cudaMemcpyAsync(h->sbuf[i], h->kid_host[b], kid->pitch_s * kid->nsnps, cudaMemcpyHostToDevice,
-                  h->copy);
-  cudaEventRecord(h->ev_copied[i], h->copy);
-  cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0);
-  kid->d_gs = h->sbuf[i];
-  kid->tm_s = kid->tm_s_alt[i];
-  kid->tm_f = kid->tm_f_alt[i];
-}
-void stream_done(fpb_handle* h, size_t b) {
-  cudaEventRecord(h->ev_done[b & 1], h->stream);
-  h->launches += h->kids[b]->launches;
-  h->kids[b]->launches = 0;
-}
-
-void streaming_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
-  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
-  for (size_t b = 0; b < h->kids.size(); b++) {
-    stream_in(h, b);
-    launch_perform_op(h->kids[b], d_x, b == 0 ? d_y : h->d_ytmp);
-    if (b > 0) {
-      k_axpy1<<<gb, 256, 0, h->stream>>>(d_y, h->d_ytmp, h->n);  // block order, like upstream
-      h->launches++;
-    }
-    stream_done(h, b);
-  }
-}
-void streaming_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
-  for (size_t b = 0; b < h->kids.size(); b++) {
-    stream_in(h, b);
-    launch_crossprod(h->kids[b], d_x, d_t + h->kid_off[b]);
-    stream_done(h, b);
-  }
-}
-void streaming_prod(fpb_handle* h, const double* d_v, double* d_y) {
-  const uint32_t gb = (uint32_t)((h->n + 255) / 256);
-  for (size_t b = 0; b < h->kids.size(); b++) {
-    stream_in(h, b);
-    launch_prod(h->kids[b], d_v + h->kid_off[b], b == 0 ? d_y : h->d_ytmp);
-    if (b > 0) {
-      k_axpy1<<<gb, 256, 0, h->stream>>>(d_y, h->d_ytmp, h->n);
-      h->launches++;
-    }
-    stream_done(h, b);
-  }
-}
+#include "fpb_host_streaming.inl"
 
 }  // namespace
 
@@ -1410,104 +1114,7 @@ int fpb_create_from_file(fpb_handle** out, const char* bed_path, uint64_t n, uin
   return 0;
 }
 
-int fpb_create_streaming(fpb_handle** out, const char* bed_path, uint64_t n, uint64_t snp_begin,
-                         uint64_t snp_count, uint64_t snps_per_slab, int stand_method,
-                         const double* preloaded_meansd, int device) {
-  if (!out || !bed_path) FPB_FAIL((fpb_handle*)nullptr, "null argument");
-  *out = nullptr;
-  if (n == 0) FPB_FAIL((fpb_handle*)nullptr, "empty genotype matrix (N == 0 or nsnps == 0)");
-  if (snps_per_slab == 0) FPB_FAIL((fpb_handle*)nullptr, "snps_per_slab must be positive");
-  {
-    const char* gv = getenv("FPB_GEMV");
-    if (gv && (!strcmp(gv, "ldg") || !strcmp(gv, "tma2")))
-      FPB_FAIL((fpb_handle*)nullptr, "streaming mode needs the single-copy kernels (unset FPB_GEMV)");
-  }
-  FILE* f = fopen(bed_path, "rb");
-  if (!f)
-    FPB_FAIL((fpb_handle*)nullptr, std::string("[Data::read_bed] Error reading file ") + bed_path +
-                                       ", error " + strerror(errno));
-  fseeko(f, 0, SEEK_END);
-  const uint64_t fsz = (uint64_t)ftello(f);
-  fclose(f);
-  const uint64_t np = (n + 3) / 4, file_snps = (fsz >= 3 ? fsz - 3 : 0) / np;  // data.cpp:163-170
-  if (snp_begin > file_snps) snp_begin = file_snps;
-  if (snp_count == 0 || snp_begin + snp_count > file_snps) snp_count = file_snps - snp_begin;
-  if (snp_count == 0) FPB_FAIL((fpb_handle*)nullptr, "empty genotype matrix (N == 0 or nsnps == 0)");
-
-  fpb_handle* h = new fpb_handle();
-  int rc = [&]() -> int {
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-      FPB_FAIL(h, std::string("no usable CUDA device (flashpca_b200 has no CPU fallback): ") +
-                      cudaGetErrorString(e));
-    if (device < 0 || device >= ndev) FPB_FAIL(h, "invalid CUDA device ordinal");
-    h->device = device;
-    FPB_CUDA(h, cudaSetDevice(device));
-    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    FPB_CUDA(h, cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-      FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
-      FPB_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-    }
-    h->n = n;
-    h->nsnps = snp_count;
-    h->np = np;
-    h->pitch_s = (np + 63) / 64 * 64;
-    h->stand_method = stand_method;
-    const uint64_t slab = std::min(snps_per_slab, snp_count);
-    for (int i = 0; i < 2; i++) FPB_CUDA(h, cudaMalloc(&h->sbuf[i], h->pitch_s * slab));
-    FPB_CUDA(h, cudaMalloc(&h->d_ytmp, sizeof(double) * n));
-    std::vector<double> msd;
-    for (uint64_t off = 0; off < snp_count; off += slab) {
-      const uint64_t cnt = std::min(slab, snp_count - off);
-      const double* kid_msd = nullptr;
-      if (preloaded_meansd) {  // nsnps x 2 column-major -> the slab's cnt x 2
-        msd.resize(2 * cnt);
-        std::copy(preloaded_meansd + off, preloaded_meansd + off + cnt, msd.begin());
-        std::copy(preloaded_meansd + snp_count + off, preloaded_meansd + snp_count + off + cnt,
-                  msd.begin() + cnt);
-        kid_msd = msd.data();
-      }
-      fpb_handle* kid = nullptr;
-      if (fpb_create_from_file(&kid, bed_path, n, snp_begin + off, cnt, stand_method, kid_msd,
-                               device))
-        FPB_FAIL(h, g_err);
-      h->kids.push_back(kid);
-      h->kid_off.push_back(off);
-      h->kid_host.push_back(nullptr);
-      // the recoded genotypes leave HBM: pinned host memory is their home from now on
-      FPB_CUDA(h, cudaMallocHost(&h->kid_host.back(), kid->pitch_s * cnt));
-      FPB_CUDA(h, cudaMemcpy(h->kid_host.back(), kid->d_gs, kid->pitch_s * cnt,
-                             cudaMemcpyDeviceToHost));
-      cudaFree(kid->d_gs);
-      kid->d_gs = nullptr;
-      if (kid->use_imma && kid->use_tma)
-        for (int i = 0; i < 2; i++) {
-          if (make_tensor_map(kid, h->sbuf[i], kid->pitch_s, cnt, &kid->tm_s_alt[i]) ||
-              make_tensor_map(kid, h->sbuf[i], kid->pitch_s, cnt, &kid->tm_f_alt[i], fpb::kFRows))
-            FPB_FAIL(h, kid->err);
-        }
-      cudaStreamDestroy(kid->stream);
-      cudaStreamDestroy(kid->side);
-      kid->stream = h->stream;
-      kid->side = h->side;
-      kid->borrowed = true;
-      h->trace += kid->trace;  // slab order, like the block loop of svdwide.cpp:44-61
-      h->launches += kid->launches;
-      kid->launches = 0;
-    }
-    return 0;
-  }();
-  if (rc) {
-    g_err = h->err;
-    fpb_destroy(h);
-    return 1;
-  }
-  *out = h;
-  return 0;
-}
+#include "fpb_host_streaming_create.inl"
 
 int fpb_create_synthetic(fpb_handle** out, uint64_t n, uint64_t nsnps, uint64_t snp_offset,
                          const unsigned char* pop_of_individual, const uint32_t* thresholds,
