@@ -167,6 +167,7 @@ struct fpb_handle {
   std::vector<uint8_t*> kid_host;          // pinned recoded genotypes of each kid (pitch_s x nsnps_kid)
   std::vector<uint64_t> kid_off;           // first SNP of each kid
   uint8_t* sbuf[2] = {nullptr, nullptr};
+  long long sbuf_holds[2] = {-1, -1};       // slab currently resident in each buffer
   fpb::TmaDesc tm_s_alt[2], tm_f_alt[2];   // kid: tensor maps over the parent's two slab buffers
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};

@@ -14,10 +14,13 @@ __global__ void k_axpy1(double* __restrict__ y, const double* __restrict__ t, ui
 void stream_in(fpb_handle* h, size_t b) {
   const int i = (int)(b & 1);
   fpb_handle* kid = h->kids[b];
-  cudaStreamWaitEvent(h->copy, h->ev_done[i], 0);  // kernels of slab b - 2 are done with the buffer
-  cudaMemcpyAsync(h->sbuf[i], h->kid_host[b], kid->pitch_s * kid->nsnps, cudaMemcpyHostToDevice,
-                  h->copy);
-  cudaEventRecord(h->ev_copied[i], h->copy);
+  if (h->sbuf_holds[i] != (long long)b) {  // (with one or two slabs everything stays resident)
+    cudaStreamWaitEvent(h->copy, h->ev_done[i], 0);  // kernels of slab b - 2 are done with the buffer
+    cudaMemcpyAsync(h->sbuf[i], h->kid_host[b], kid->pitch_s * kid->nsnps, cudaMemcpyHostToDevice,
+                    h->copy);
+    cudaEventRecord(h->ev_copied[i], h->copy);
+    h->sbuf_holds[i] = (long long)b;
+  }
   cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0);
   kid->d_gs = h->sbuf[i];
   kid->tm_s = kid->tm_s_alt[i];

@@ -48,6 +48,7 @@ int fpb_create_streaming(fpb_handle** out, const char* bed_path, uint64_t n, uin
     const uint64_t slab = std::min(snps_per_slab, snp_count);
     for (int i = 0; i < 2; i++) FPB_CUDA(h, cudaMalloc(&h->sbuf[i], h->pitch_s * slab));
     FPB_CUDA(h, cudaMalloc(&h->d_ytmp, sizeof(double) * n));
+    FPB_CUDA(h, cudaMalloc(&h->d_t, sizeof(double) * snp_count));  // fpb_time_perform_op's X'x scratch
     std::vector<double> msd;
     for (uint64_t off = 0; off < snp_count; off += slab) {
       const uint64_t cnt = std::min(slab, snp_count - off);
