@@ -158,3 +158,36 @@ def test_save_text_format_matches_iostream_general(native_lib, tmp_path):
     vals = [1.0, 0.1234567891234, 123456789.0, 1e-10, -2.5e-7, 3.0e22]
     want7 = ["1", "0.1234568", "1.234568e+08", "1e-10", "-2.5e-07", "3e+22"]
     assert ["%.7g" % v for v in vals] == want7   # %.{p}g is the iostream general format
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port of the path, no GPU): one JSON
+    line with the keys the measurement contract names."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")   # what torchrun exports to its workers
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--n", "4000", "--p", "300", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference"
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["value"] > 0 and line["unit"] == "genotypes/s" and line["vs_baseline"] is None
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == line["value"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))      # all host threads despite OMP_NUM_THREADS=1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_native_artefacts_build_and_link():
+    """build.py produces the library, the flashpca front end and the flashpcaR
+    entry-point driver (link check; none of them is run without a GPU)."""
+    from flashpca_b200 import build
+    build.build_lib()
+    assert os.path.exists(build.build_cli())
+    assert os.path.exists(build.build_rapi_check())
