@@ -39,6 +39,7 @@
 #include "fpb_imma.cuh"
 #include "fpb_irlm.cuh"
 #include "fpb_kernels.cuh"
+#include "fpb_umma.cuh"
 
 namespace {
 
@@ -161,6 +162,19 @@ struct fpb_handle {
     uint32_t nparts = 0;
   } L1;
   size_t slice_bytes = 0, part_elems = 0, max_parts = 0;
+  // tcgen05 block path (fpb_umma.cuh, fpb_host_umma.inl): 8 lanes of per-vector scratch, allocated
+  // on the first block call with k >= 3
+  struct Umma {
+    bool ready = false, used = false;
+    uint8_t *s_i = nullptr, *s_j = nullptr;      // digit slices of the two halves, all lanes interleaved
+    double *part = nullptr, *a = nullptr, *corr = nullptr, *pmax = nullptr, *psum = nullptr;
+    double *mx = nullptr, *mc = nullptr;
+    fpb::VecScale* sc = nullptr;                  // [lane] first half, [8 + lane] second half
+    uint32_t* err = nullptr;                      // watchdog word
+    uint32_t nst = 0, splits_t = 1, sps_t = 1, nbox = 0, splits_v = 1, bps_v = 1;
+    uint64_t sstride_t = 0, sstride_v = 0, vstride = 0;
+    size_t si_bytes = 0, sj_bytes = 0;
+  } U;
   // out-of-HBM streaming (fpb_create_streaming): the parent owns SNP slabs ("kids": ordinary
   // handles whose genotypes live in pinned host memory), two device slab buffers and a copy stream
   std::vector<fpb_handle*> kids;
@@ -910,6 +924,14 @@ void imma_prod_tail(fpb_handle* h, double* d_y) {
 
 #include "fpb_host_pairs.inl"
 
+#include "fpb_host_umma.inl"
+
+// device-reported protocol failures of the persistent / tcgen05 kernels, at the API's sync points
+int check_async(fpb_handle* h) {
+  if (check_fused(h)) return 1;
+  return check_umma(h);
+}
+
 // in-memory matrix path (svdwide.cpp:4-12)
 void dense_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
   fpb::k_dense_gemv_t<<<(uint32_t)h->nsnps, 256, 0, h->stream>>>(h->d_X, h->n, d_x, d_t);
@@ -1262,6 +1284,7 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_sc);
   cudaFree(h->d_mx);
   cudaFree(h->d_mc);
+  free_umma(h);
   cudaFree(h->L1.slices);
   cudaFree(h->L1.part);
   cudaFree(h->L1.a);
@@ -1347,7 +1370,7 @@ int fpb_sync(fpb_handle* h) {
   if (!h) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
   FPB_CUDA(h, cudaGetLastError());
-  return check_fused(h);
+  return check_async(h);
 }
 
 // ------------------------------ device-pointer ops -------------------------
@@ -1356,7 +1379,13 @@ int fpb_crossprod_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, double
   if (!h || !d_m || !d_y || k == 0) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
   uint32_t c = 0;
-  if (k >= 2 && pair_capable(h)) {
+  if (k >= 3 && umma_capable(h)) {
+    if (ensure_umma(h)) return 1;
+    for (; k - c >= 3; c += std::min(kUmmaLanes, k - c))
+      umma_crossprod_block(h, d_m + (uint64_t)c * h->n, std::min(kUmmaLanes, k - c),
+                           d_y + (uint64_t)c * h->nsnps, false);
+  }
+  if (k - c >= 2 && pair_capable(h)) {
     if (ensure_lane1(h)) return 1;
     for (; c + 1 < k; c += 2)
       imma_crossprod_pair(h, d_m + (uint64_t)c * h->n, d_m + (uint64_t)(c + 1) * h->n,
@@ -1371,7 +1400,14 @@ int fpb_prod_multi_dev(fpb_handle* h, const double* d_v, uint32_t k, double* d_y
   if (!h || !d_v || !d_y || k == 0) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
   uint32_t c = 0;
-  if (k >= 2 && pair_capable(h)) {
+  if (k >= 3 && umma_capable(h)) {
+    if (ensure_umma(h)) return 1;
+    for (; k - c >= 3; c += std::min(kUmmaLanes, k - c)) {
+      umma_prod_inputs(h, d_v + (uint64_t)c * h->nsnps, std::min(kUmmaLanes, k - c));
+      umma_prod_block(h, std::min(kUmmaLanes, k - c), d_y + (uint64_t)c * h->n);
+    }
+  }
+  if (k - c >= 2 && pair_capable(h)) {
     if (ensure_lane1(h)) return 1;
     for (; c + 1 < k; c += 2) {
       prod_inputs_pair(h, d_v + (uint64_t)c * h->nsnps, d_v + (uint64_t)(c + 1) * h->nsnps);
@@ -1387,7 +1423,14 @@ int fpb_perform_op_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, doubl
   if (!h || !d_m || !d_y || k == 0) FPB_FAIL(h, "null argument");
   FPB_CUDA(h, cudaSetDevice(h->device));
   uint32_t c = 0;
-  if (k >= 2 && pair_capable(h) && !h->use_fused) {
+  if (k >= 3 && umma_capable(h)) {
+    if (ensure_umma(h)) return 1;
+    for (; k - c >= 3; c += std::min(kUmmaLanes, k - c)) {
+      umma_crossprod_block(h, d_m + (uint64_t)c * h->n, std::min(kUmmaLanes, k - c), nullptr, true);
+      umma_prod_block(h, std::min(kUmmaLanes, k - c), d_y + (uint64_t)c * h->n);
+    }
+  }
+  if (k - c >= 2 && pair_capable(h) && !h->use_fused) {
     if (ensure_lane1(h)) return 1;
     for (; c + 1 < k; c += 2) {
       imma_crossprod_pair(h, d_m + (uint64_t)c * h->n, d_m + (uint64_t)(c + 1) * h->n, nullptr,
@@ -1418,7 +1461,7 @@ static int host_op(fpb_handle* h, const double* in, uint32_t k, double* out, uin
   FPB_CUDA(h, cudaMemcpyAsync(out, h->d_out, sizeof(double) * out_rows * k,
                               cudaMemcpyDeviceToHost, h->stream));
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
-  return check_fused(h);
+  return check_async(h);
 }
 
 int fpb_perform_op_multi(fpb_handle* h, const double* m_in, uint32_t k, double* y_out) {
@@ -1526,7 +1569,7 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
     cudaEventDestroy(evs[i]);
     cudaEventDestroy(evs[i + 1]);
   }
-  if (op_rc || check_fused(h)) {
+  if (op_rc || check_async(h)) {
     solver.set_op(nullptr);
     return 1;
   }
@@ -1618,7 +1661,7 @@ int fpb_time_perform_op(fpb_handle* h, const double* d_x, double* d_y, uint32_t 
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   FPB_CUDA(h, cudaGetLastError());
-  return check_fused(h);
+  return check_async(h);
 }
 
 int fpb_fused_debug(fpb_handle* h, unsigned long long* out, uint64_t count) {

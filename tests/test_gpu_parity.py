@@ -712,11 +712,12 @@ def test_streaming_preloaded_meansd_and_shard(native_lib, path):
 
 
 def test_two_vector_kernels_match_single_vector_path(native_lib, monkeypatch):
-    """The block variants take their columns two at a time (k_imma_gemv_tma_2v /
-    _t_2v, odd column counts leave one for the single-vector kernels); FPB_PAIR=0
-    loops over columns.  Same integer sums: results agree to the FP64 recombination."""
+    """Without the tcgen05 block path (FPB_UMMA=0) the block variants take their columns two at a
+    time (k_imma_gemv_tma_2v / _t_2v, odd column counts leave one for the single-vector kernels);
+    FPB_PAIR=0 loops over columns.  Same integer sums: results agree to the FP64 recombination."""
     monkeypatch.delenv("FPB_PATH", raising=False)
     monkeypatch.delenv("FPB_GEMV", raising=False)
+    monkeypatch.setenv("FPB_UMMA", "0")
     from flashpca_b200.synth import SynthSpec
     s = SynthSpec(40003, 2501, seed=11, missing_rate=0.003)
     rng = np.random.default_rng(5)
@@ -734,6 +735,84 @@ def test_two_vector_kernels_match_single_vector_path(native_lib, monkeypatch):
     sub = s.create_operator(j0=0, j1=64)
     orc = O.COracle(s.packed_bed(0, 64), s.n, 64)
     assert _relerr(sub.perform_op_mat(m), orc.perform_op(m, 0)) <= OP_RTOL
+
+
+@pytest.mark.parametrize("name", ["data_chr1", "hapmap3"])
+@pytest.mark.parametrize("k", [3, 4, 7, 8, 20])
+def test_tcgen05_block_ops_vs_oracle(native_lib, monkeypatch, name, k):
+    """Block variants with k >= 3 columns (perform_op_mat / crossprod2 / prod3,
+    svdwide.cpp:71-118, 157-188, 312-343) run on the tcgen05 kernels (fpb_umma.cuh), 8 or 4 columns
+    per pass; k = 20 is the loadings / --check / --project shape of a 20-dimensional PCA."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    monkeypatch.delenv("FPB_GEMV", raising=False)
+    monkeypatch.delenv("FPB_UMMA", raising=False)
+    _, payload, n, p = load_fixture(name)
+    op = _mk(payload, n, p)
+    orc = O.COracle(payload, n, p)
+    rng = np.random.default_rng(100 + k)
+    m = rng.standard_normal((n, k)) * np.exp(rng.uniform(-30, 30, size=k))   # one scale per column
+    w = rng.standard_normal((p, k)) * np.exp(rng.uniform(-30, 30, size=k))
+    y = op.perform_op_mat(m)
+    y_ref = orc.perform_op(m, 0)
+    t, t_ref = op.crossprod2(m), orc.crossprod(m, 0)
+    z, z_ref = op.prod3(w), orc.prod(w, 0)
+    for j in range(k):
+        assert _relerr(y[:, j], y_ref[:, j]) <= OP_RTOL
+        assert _relerr(t[:, j], t_ref[:, j]) <= OP_RTOL
+        assert _relerr(z[:, j], z_ref[:, j]) <= OP_RTOL
+    assert np.array_equal(op.perform_op_mat(m), y)          # bit-reproducible
+    op.close()
+
+
+def test_tcgen05_block_ops_match_single_vector_path(native_lib, monkeypatch):
+    """Same integer sums as the mma.sync kernels: per column the block result equals the
+    single-vector op to the FP64 recombination order; ragged N and P, missing genotypes, dead
+    columns, a zero and a NaN vector in the block."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    monkeypatch.delenv("FPB_GEMV", raising=False)
+    monkeypatch.delenv("FPB_UMMA", raising=False)
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(40003, 2501, seed=11, missing_rate=0.003)
+    rng = np.random.default_rng(5)
+    m = rng.standard_normal((s.n, 11))
+    v = rng.standard_normal((s.p, 6))
+    m[:, 1] *= 1e-40
+    m[:, 4] = 0.0
+    op = s.create_operator()
+    y, t, z = op.perform_op_mat(m), op.crossprod2(m), op.prod3(v)
+    assert np.array_equal(y[:, 4], np.zeros(s.n)) and np.array_equal(t[:, 4], np.zeros(s.p))
+    for j in range(11):
+        assert _relerr(y[:, j], op.perform_op(m[:, j])) <= 1e-13
+        assert _relerr(t[:, j], op.crossprod(m[:, j])) <= 1e-13
+    for j in range(6):
+        assert _relerr(z[:, j], op.prod(v[:, j])) <= 1e-13
+    m[7, 2] = np.nan
+    y = op.perform_op_mat(m)
+    assert np.isnan(y[:, 2]).all() and np.isfinite(np.delete(y, 2, axis=1)).all()
+    sub = s.create_operator(j0=0, j1=64)
+    orc = O.COracle(s.packed_bed(0, 64), s.n, 64)
+    assert _relerr(sub.perform_op_mat(m[:, :2].repeat(2, axis=1)), orc.perform_op(m[:, :2].repeat(2, axis=1), 0)) <= OP_RTOL
+
+
+@pytest.mark.parametrize("n,p", [(1, 5), (3, 1), (129, 517), (513, 130), (2049, 1025), (70001, 300)])
+def test_tcgen05_block_ops_ragged(native_lib, monkeypatch, n, p):
+    """Edge shapes through the tcgen05 block kernels: fewer rows than one 128-row box, one
+    individual, N just past a 512-individual stage, several column splits (N > 65536)."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    monkeypatch.delenv("FPB_UMMA", raising=False)
+    rng = np.random.default_rng(n * 31 + p)
+    codes = rng.integers(0, 4, size=(n, p), dtype=np.uint8)
+    if n > 2:
+        codes[:, 0] = 3          # monomorphic column (PLINK 11 = dosage 0 everywhere)
+    payload = _pack(codes)
+    op = _mk(payload, n, p)
+    orc = O.COracle(payload, n, p)
+    m = rng.standard_normal((n, 5))
+    w = rng.standard_normal((p, 5))
+    assert _relerr(op.perform_op_mat(m), orc.perform_op(m, 0)) <= OP_RTOL
+    assert _relerr(op.crossprod2(m), orc.crossprod(m, 0)) <= OP_RTOL
+    assert _relerr(op.prod3(w), orc.prod(w, 0)) <= OP_RTOL
+    op.close()
 
 
 def test_device_memory_query(native_lib):

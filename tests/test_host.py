@@ -21,6 +21,20 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert native_lib.fpb_abi_version() == 1
 
 
+def test_product_library_carries_blackwell_native_code(native_lib):
+    """SASS of the built product library: TMA (UTMALDG / UBLKCP), byte-transposing LDSM, and the
+    tcgen05 block kernels (UTCIMMA = tcgen05.mma kind::i8, STTM / LDTM = tcgen05.st / .ld)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from flashpca_b200 import build
+    sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCIMMA", "STTM", "LDTM", "UTMALDG", "UBLKCP", "LDSM.8.MT1616", "IMMA"):
+        assert mnemonic in sass, mnemonic
+
+
 def test_no_cuda_means_loud_failure(native_lib):
     """Without a GPU the product path must fail, never fall back to a CPU path."""
     import torch
