@@ -49,9 +49,11 @@ SIGNATURES = {
     "fpb_comm_init": (_i, [_vp, _vp, _i, _i]),
     "fpb_pca": (_i, [_vp, _u32, _u32, _u32, _d, _vp, _vp, _c.POINTER(_u32), _c.POINTER(_u32),
                      _c.POINTER(_u32)]),
+    "fpb_pca_residual": (_i, [_vp, _d, _vp, _u32]),
     "fpb_pca_op_times": (_u32, [_vp, _vp, _u32]),
     "fpb_pca_phase_times": (None, [_vp, _vp]),
     "fpb_time_perform_op": (_i, [_vp, _vp, _vp, _u32, _c.POINTER(_c.c_float), _vp]),
+    "fpb_time_perform_op_steps": (_i, [_vp, _vp, _vp, _u32, _vp]),
     "fpb_launch_count": (_u64, [_vp]),
     "fpb_path_info": (_c.c_uint, [_vp]),
     "fpb_device_memory": (_i, [_i, _c.POINTER(_u64), _c.POINTER(_u64)]),

@@ -199,6 +199,7 @@ struct fpb_handle {
   int nranks = 1, rank = 0;
   uint64_t launches = 0;
   std::vector<float> op_ms;
+  std::vector<double> last_evals;  // Ritz values of the last fpb_pca call (fpb_pca_residual)
   fpb::Irlm* solver = nullptr;  // Lanczos workspace, kept between fpb_pca calls
   // fpb_time_perform_op: events bracketing the two contraction-kernel launches
   bool time_gemv = false;
@@ -1530,8 +1531,8 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
             double* evals_out, double* evecs_out, uint32_t* nconv_out, uint32_t* nops_out,
             uint32_t* niter_out) {
   if (!h) FPB_FAIL(h, "null argument");
-  if (nev < 1 || ncv <= nev || ncv > h->n || ncv > (uint32_t)fpb::kMaxNcv)
-    FPB_FAIL(h, "invalid nev/ncv (need 1 <= nev < ncv <= min(N, 128))");
+  if (nev < 1 || ncv <= nev || ncv > h->n)
+    FPB_FAIL(h, "invalid nev/ncv (need 1 <= nev < ncv <= N)");
   FPB_CUDA(h, cudaSetDevice(h->device));
   h->op_ms.clear();
   std::vector<cudaEvent_t> evs;
@@ -1579,6 +1580,7 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
   }
   FPB_CUDA(h, cudaGetLastError());
   if (evals_out) memcpy(evals_out, res.evals.data(), sizeof(double) * nev);
+  h->last_evals = res.evals;
   auto t2 = t1, t3 = t1;
   if (evecs_out) {
     if (ensure_staging(h, 0, (size_t)h->n * nev)) return 1;
@@ -1599,6 +1601,27 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
   if (niter_out) *niter_out = res.niter;
   FPB_CUDA(h, cudaGetLastError());
   return 0;
+}
+
+int fpb_pca_residual(fpb_handle* h, double div, double* err_out, uint32_t nev) {
+  if (!h || !err_out || !(div > 0.0)) FPB_FAIL(h, "null argument");
+  if (!h->solver || h->last_evals.size() != nev || nev == 0)
+    FPB_FAIL(h, "fpb_pca_residual: no fpb_pca result with this many eigenvectors on the handle");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  if (ensure_staging(h, (size_t)h->n * nev + nev, (size_t)h->n * nev + nev)) return 1;
+  h->solver->eigenvectors(h->d_in);  // U, N x nev
+  if (fpb_perform_op_multi_dev(h, h->d_in, nev, h->d_out)) return 1;  // all-reduced when sharded
+  double* d_lam = h->d_in + (size_t)h->n * nev;
+  double* d_err = h->d_out + (size_t)h->n * nev;
+  FPB_CUDA(h, cudaMemcpyAsync(d_lam, h->last_evals.data(), sizeof(double) * nev,
+                              cudaMemcpyHostToDevice, h->stream));
+  fpb::k_check_resid<<<nev, 1024, 0, h->stream>>>(h->d_out, h->d_in, d_lam, h->n, div, d_err);
+  h->launches++;
+  FPB_CUDA(h, cudaMemcpyAsync(err_out, d_err, sizeof(double) * nev, cudaMemcpyDeviceToHost,
+                              h->stream));
+  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  FPB_CUDA(h, cudaGetLastError());
+  return check_async(h);
 }
 
 void fpb_pca_phase_times(const fpb_handle* h, double out_seconds[4]) {
@@ -1660,6 +1683,24 @@ int fpb_time_perform_op(fpb_handle* h, const double* d_x, double* d_y, uint32_t 
     }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+  FPB_CUDA(h, cudaGetLastError());
+  return check_async(h);
+}
+
+int fpb_time_perform_op_steps(fpb_handle* h, const double* d_x, double* d_y, uint32_t reps,
+                              float* ms_each_out) {
+  if (!h || !d_x || !d_y || !ms_each_out || reps == 0) FPB_FAIL(h, "null argument");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  std::vector<cudaEvent_t> ev(reps + 1);
+  for (auto& e : ev) FPB_CUDA(h, cudaEventCreate(&e));
+  FPB_CUDA(h, cudaEventRecord(ev[0], h->stream));
+  for (uint32_t r = 0; r < reps; r++) {
+    if (fpb_perform_op_dev(h, d_x, d_y)) return 1;
+    FPB_CUDA(h, cudaEventRecord(ev[r + 1], h->stream));
+  }
+  FPB_CUDA(h, cudaEventSynchronize(ev[reps]));
+  for (uint32_t r = 0; r < reps; r++) cudaEventElapsedTime(&ms_each_out[r], ev[r], ev[r + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
   FPB_CUDA(h, cudaGetLastError());
   return check_async(h);
 }

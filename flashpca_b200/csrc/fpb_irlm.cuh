@@ -29,7 +29,7 @@
 
 namespace fpb {
 
-constexpr int kMaxNcv = 128;      // columns handled by the tall-skinny kernels
+constexpr int kMaxNcv = 128;      // columns one launch of the tall-skinny kernels handles (host loops)
 constexpr int kRowsPerBlock = 2048;
 
 // partial[g * m + c] = sum over rows of block g of V[r + c*ld] * f[r]
@@ -192,7 +192,36 @@ k_tall_times_small(const double* __restrict__ V, uint64_t ld, uint32_t m,
   }
 }
 
-// Fallback for m > MAXM of the register-cached kernel above.
+// m > MAXM of the register-cached kernel above: the product is accumulated over K-tiles of KT
+// columns of V (one launch per tile).  out (+)= V[:, k0:k0+kt] * Q[k0:k0+kt, c0:c0+nc]; the Q tile
+// sits in shared memory (kt x nc doubles), a thread keeps its KT values of the V row in registers.
+template <int KT>
+__global__ void __launch_bounds__(128)
+k_tall_times_small_tile(const double* __restrict__ V, uint64_t ld, uint32_t k0, uint32_t kt,
+                        const double* __restrict__ Q, uint32_t ldq, uint32_t c0, uint32_t nc,
+                        double* __restrict__ out, uint64_t ldo, uint64_t n, int accumulate) {
+  extern __shared__ double qs[];
+  for (uint32_t e = threadIdx.x; e < kt * nc; e += blockDim.x) {
+    const uint32_t c = e / kt, k = e - c * kt;
+    qs[e] = Q[(k0 + k) + (uint64_t)(c0 + c) * ldq];
+  }
+  __syncthreads();
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double vr[KT];
+#pragma unroll
+  for (int k = 0; k < KT; k++) vr[k] = (uint32_t)k < kt ? V[r + (uint64_t)(k0 + k) * ld] : 0.0;
+  for (uint32_t c = 0; c < nc; c++) {
+    const double* qc = qs + c * kt;
+    double s = accumulate ? out[r + (uint64_t)(c0 + c) * ldo] : 0.0;
+#pragma unroll
+    for (int k = 0; k < KT; k++)
+      if ((uint32_t)k < kt) s += vr[k] * qc[k];
+    out[r + (uint64_t)(c0 + c) * ldo] = s;
+  }
+}
+
+// Reference form (kept for cross-checks).
 __global__ void __launch_bounds__(128)
 k_tall_times_small_generic(const double* __restrict__ V, uint64_t ld, uint32_t m,
                            const double* __restrict__ Q, uint32_t ldq, uint32_t nc,
@@ -203,6 +232,33 @@ k_tall_times_small_generic(const double* __restrict__ V, uint64_t ld, uint32_t m
     double s = 0.0;
     for (uint32_t k = 0; k < m; k++) s += V[r + (uint64_t)k * ld] * Q[k + (uint64_t)c * ldq];
     out[r + (uint64_t)c * ldo] = s;
+  }
+}
+
+// err[c] = sum_r (Y[r, c] / div - U[r, c] lambda[c] / div)^2: the per-eigenvector squared residual
+// of RandomPCA::check (randompca.cpp:663-703).  One block per column, fixed summation order.
+__global__ void __launch_bounds__(1024)
+k_check_resid(const double* __restrict__ Y, const double* __restrict__ U,
+              const double* __restrict__ lambda, uint64_t n, double div, double* __restrict__ err) {
+  __shared__ double sh[32];
+  const uint32_t c = blockIdx.x;
+  const double d = lambda[c] / div;
+  const double* y = Y + (uint64_t)c * n;
+  const double* u = U + (uint64_t)c * n;
+  double s = 0.0;
+  for (uint64_t r = threadIdx.x; r < n; r += 1024) {
+    const double e = y[r] / div - u[r] * d;
+    s += e * e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = sh[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) err[c] = s;
   }
 }
 
@@ -366,12 +422,27 @@ class Irlm {
   void retrieve_ritzpair();
   // d_out (N x nc) = V (N x ncv) * dQ (ncv x nc)
   void tall_times_small(const double* dQ, uint32_t nc, double* d_out) {
-    if (ncv_ <= 48)
+    if (ncv_ <= 48) {
       k_tall_times_small<48><<<grid1d(128), 128, sizeof(double) * ncv_ * nc, stream_>>>(
           dV_, n_, ncv_, dQ, ncv_, nc, d_out, n_, n_);
-    else
-      k_tall_times_small_generic<<<grid1d(128), 128, 0, stream_>>>(dV_, n_, ncv_, dQ, ncv_, nc,
-                                                                   d_out, n_, n_);
+      return;
+    }
+    // any ncv (ndim up to (min(N, P) - 1) / 2, flashpca.cpp:623-633): K-tiles of 64 columns of V,
+    // column tiles of 64 outputs (32 KB of shared memory per launch)
+    constexpr uint32_t KT = 64, CT = 64;
+    for (uint32_t c0 = 0; c0 < nc; c0 += CT)
+      for (uint32_t k0 = 0; k0 < ncv_; k0 += KT) {
+        const uint32_t kt = std::min(KT, ncv_ - k0), ct = std::min(CT, nc - c0);
+        k_tall_times_small_tile<KT><<<grid1d(128), 128, sizeof(double) * kt * ct, stream_>>>(
+            dV_, n_, k0, kt, dQ, ncv_, c0, ct, d_out, n_, n_, k0 > 0);
+      }
+  }
+  // f -= V[:, :m] h for any m (chunks of kMaxNcv columns; h on the device)
+  void gemv_n_sub(uint32_t m, const double* d_h) {
+    for (uint32_t c0 = 0; c0 < m; c0 += kMaxNcv)
+      k_gemv_n_sub<<<grid1d(256), 256, 0, stream_>>>(dV_ + (uint64_t)c0 * n_, n_,
+                                                      std::min<uint32_t>(kMaxNcv, m - c0), d_h + c0,
+                                                      dF_, n_);
   }
   double& H(uint32_t r, uint32_t c) { return H_[(size_t)c * ncv_ + r]; }
   double* col(uint32_t i) { return dV_ + (uint64_t)i * n_; }
@@ -427,8 +498,12 @@ inline void Irlm::release() {
 }
 
 inline void Irlm::gemv_t(const double* V, uint32_t m, const double* f, double* host_out) {
-  k_gemv_t_partial<<<nblocks_, 256, 0, stream_>>>(V, n_, m, f, n_, dPartial_);
-  k_gemv_t_final<<<(m * 32 + 255) / 256, 256, 0, stream_>>>(dPartial_, nblocks_, m, dSmall_);
+  for (uint32_t c0 = 0; c0 < m; c0 += kMaxNcv) {  // the partial kernel handles kMaxNcv columns
+    const uint32_t mc = std::min<uint32_t>(kMaxNcv, m - c0);
+    double* part = dPartial_ + (uint64_t)nblocks_ * c0;
+    k_gemv_t_partial<<<nblocks_, 256, 0, stream_>>>(V + (uint64_t)c0 * n_, n_, mc, f, n_, part);
+    k_gemv_t_final<<<(mc * 32 + 255) / 256, 256, 0, stream_>>>(part, nblocks_, mc, dSmall_ + c0);
+  }
   cudaMemcpyAsync(host_out, dSmall_, sizeof(double) * m, cudaMemcpyDeviceToHost, stream_);
   cudaStreamSynchronize(stream_);
 }
@@ -465,7 +540,7 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
       cudaMemcpyAsync(dF_, rnd.data(), sizeof(double) * n_, cudaMemcpyHostToDevice, stream_);
       gemv_t(dV_, i, dF_, Vf.data());
       cudaMemcpyAsync(dSmall_, Vf.data(), sizeof(double) * i, cudaMemcpyHostToDevice, stream_);
-      k_gemv_n_sub<<<grid1d(256), 256, 0, stream_>>>(dV_, n_, i, dSmall_, dF_, n_);
+      gemv_n_sub(i, dSmall_);
       beta = norm(dF_);
       restart = true;
     }
@@ -517,7 +592,7 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
       } else {
         cudaMemcpyAsync(dSmall_, hprev.data(), sizeof(double) * i1, cudaMemcpyHostToDevice,
                         stream_);
-        k_gemv_n_sub<<<grid1d(256), 256, 0, stream_>>>(dV_, n_, i1, dSmall_, dF_, n_);
+        gemv_n_sub(i1, dSmall_);
         cudaStreamSynchronize(stream_);
         beta = norm(dF_);
         gemv_t(dV_, i1, dF_, Vf.data());

@@ -46,7 +46,7 @@ class SVDWide:
     perform_op = lambda self, x, y=None: SVDWideOnline.perform_op(self, x, y)
     crossprod2 = lambda self, x: SVDWideOnline.crossprod2(self, x)
     prod3 = lambda self, x: SVDWideOnline.prod3(self, x)
-    pca = lambda self, *a: SVDWideOnline.pca(self, *a)
+    pca = lambda self, *a, **kw: SVDWideOnline.pca(self, *a, **kw)
 
     def standardised(self) -> np.ndarray:
         out = np.zeros((self.n, self.p), order="F")
@@ -190,15 +190,24 @@ class SVDWideOnline:
         return np.asfortranarray(self.crossprod2(x).T)
 
     # -- whole solve (Lanczos basis resident in HBM)
-    def pca(self, nev: int, ncv: int, maxiter: int, tol: float):
+    def pca(self, nev: int, ncv: int, maxiter: int, tol: float, want_vectors: bool = True):
+        """want_vectors=False skips the eigenvector download (SNP-sharded runs: every rank holds
+        the same vectors, one rank needs them on the host)."""
         evals = np.zeros(nev)
-        evecs = np.zeros((self.n, nev), order="F")
+        evecs = np.zeros((self.n, nev), order="F") if want_vectors else None
         nconv, nops, niter = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         check(self.lib.fpb_pca(self.h, nev, ncv, maxiter, float(tol), evals.ctypes.data,
-                               evecs.ctypes.data, ctypes.byref(nconv), ctypes.byref(nops),
-                               ctypes.byref(niter)), self.h)
+                               evecs.ctypes.data if want_vectors else None, ctypes.byref(nconv),
+                               ctypes.byref(nops), ctypes.byref(niter)), self.h)
         return dict(values=evals, vectors=evecs, nconv=nconv.value, nops=nops.value,
                     niter=niter.value)
+
+    def pca_residual(self, nev: int, div: float) -> np.ndarray:
+        """randompca.cpp:663-703 on the solver's own eigenpairs, computed on the device:
+        err_j = ||X X' u_j / div - u_j d_j||^2 (collective when SNP-sharded)."""
+        err = np.zeros(nev)
+        check(self.lib.fpb_pca_residual(self.h, float(div), err.ctypes.data, nev), self.h)
+        return err
 
     def pca_phase_seconds(self) -> dict:
         buf = np.zeros(4)

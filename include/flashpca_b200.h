@@ -165,6 +165,14 @@ int fpb_pca(fpb_handle *h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
             double *evals_out, double *evecs_out, uint32_t *nconv_out, uint32_t *nops_out,
             uint32_t *niter_out);
 
+/* Self-check of the last fpb_pca result without leaving the device: RandomPCA::check
+ * (randompca.cpp:663-703) applied to the solver's own eigenpairs,
+ *   err_out[j] = || X X' u_j / div - u_j d_j ||^2,  d_j = lambda_j / div,  j < nev
+ * (mse = sum_j err_j / (N nev), "< 1e-8" per README.md:207).  One block call
+ * fpb_perform_op_multi_dev on the N x nev eigenvectors; collective when a communicator is
+ * attached (every rank must call it). */
+int fpb_pca_residual(fpb_handle *h, double div, double *err_out, uint32_t nev);
+
 /* Per-op device timings of the last fpb_pca call, milliseconds (CUDA events on
  * the handle's stream); returns the number written (<= cap). */
 uint32_t fpb_pca_op_times(const fpb_handle *h, float *ms_out, uint32_t cap);
@@ -184,6 +192,11 @@ void fpb_pca_phase_times(const fpb_handle *h, double out_seconds[4]);
  * alone, [1] = [3] = 0. */
 int fpb_time_perform_op(fpb_handle *h, const double *d_x, double *d_y, uint32_t reps,
                         float *ms_per_op_out, float *ms_kernels_out);
+
+/* Same op sequence with a CUDA event after every op: ms_each_out[r] (reps floats) = device time
+ * of op r.  bench.py reports mean (= total / reps) and median from these. */
+int fpb_time_perform_op_steps(fpb_handle *h, const double *d_x, double *d_y, uint32_t reps,
+                              float *ms_each_out);
 
 /* Which compute path the handle selected at staging (bit mask). */
 #define FPB_PATH_DENSE 1u       /* in-memory matrix (fpb_create_dense) */

@@ -383,3 +383,57 @@ void fo_set_num_threads(int n)
    (void)n;
 #endif
 }
+
+/* ---------------------------------------------------------------------------
+ * Synthetic input for the CPU baseline legs of bench.py: the Balding-Nichols
+ * generator of flashpca_b200/synth.py (counter-based hashing, SURVEY.md section
+ * 8d), bit for bit, so the CPU arm is timed on SNP columns of the very matrix
+ * the GPU arm holds.  Not part of the restated path; input preparation only.
+ * thresholds: npop x nsnps_total uint32 row-major, pop: N bytes.
+ * out: (j1 - j0) x ceil(N/4) packed PLINK bytes (no 3-byte header).
+ * ------------------------------------------------------------------------- */
+static unsigned long long fo_mix64(unsigned long long z)
+{
+   z += 0x9E3779B97F4A7C15ULL;
+   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+   return z ^ (z >> 31);
+}
+
+void fo_synth_bed(unsigned char *out, unsigned long long N, unsigned long long j0,
+   unsigned long long j1, unsigned long long nsnps_total, const unsigned char *pop,
+   const unsigned int *thresholds, unsigned int miss_thr, unsigned long long seed)
+{
+   const unsigned long long np = (N + 3) / 4;
+   long long jj;
+#pragma omp parallel for schedule(static)
+   for(jj = (long long)j0; jj < (long long)j1; jj++)
+   {
+      const unsigned long long j = (unsigned long long)jj;
+      unsigned char *row = out + (j - j0) * np;
+      unsigned long long b;
+      for(b = 0; b < np; b++)
+      {
+	 unsigned char byte = 0;
+	 int q;
+	 for(q = 0; q < 4; q++)
+	 {
+	    const unsigned long long i = 4 * b + q;
+	    unsigned char code = 0;
+	    if(i < N)
+	    {
+	       const unsigned long long h = fo_mix64(seed ^ fo_mix64(j * 0x100000001B3ULL + i));
+	       const unsigned int u1 = (unsigned int)h, u2 = (unsigned int)(h >> 32);
+	       const unsigned int um = (unsigned int)fo_mix64(h ^ 0xD6E8FEB86659FD93ULL);
+	       const unsigned int t = thresholds[(unsigned long long)pop[i] * nsnps_total + j];
+	       const int g = (u1 < t) + (u2 < t);
+	       code = (g == 2) ? 0 : (g == 1 ? 2 : 3);
+	       if(um < miss_thr)
+		  code = 1;
+	    }
+	    byte |= (unsigned char)(code << (2 * q));
+	 }
+	 row[b] = byte;
+      }
+   }
+}

@@ -291,6 +291,24 @@ class COracle:
 # Spectra 0.8.1 SymEigsSolver restatement (third-party; see module docstring)
 # --------------------------------------------------------------------------
 
+def synth_packed_bed(spec, j0: int, j1: int) -> np.ndarray:
+    """SNP columns [j0, j1) of a flashpca_b200.synth.SynthSpec matrix, generated on the host cores
+    by liboracle.so (same counter-based hash as synth.py / the device generator).  Input
+    preparation for the CPU baseline legs of bench.py."""
+    lib = ctypes.CDLL(build())
+    npb = (spec.n + 3) // 4
+    out = np.empty((j1 - j0) * npb, dtype=np.uint8)
+    thr = np.ascontiguousarray(spec.thresholds, dtype=np.uint32)
+    pop = np.ascontiguousarray(spec.pop, dtype=np.uint8)
+    lib.fo_synth_bed.restype = None
+    lib.fo_synth_bed.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong,
+                                 ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_uint, ctypes.c_ulonglong]
+    lib.fo_synth_bed(out.ctypes.data, spec.n, j0, j1, spec.p, pop.ctypes.data, thr.ctypes.data,
+                     spec.miss_thr, spec.seed)
+    return out
+
+
 def simple_random_vec(n: int, seed: int = 0) -> np.ndarray:
     """Spectra ``SimpleRandom<double>``: Park-Miller LCG a=16807, m=2^31-1,
     seed 0 -> 1, value/m - 0.5."""

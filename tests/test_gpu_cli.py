@@ -126,6 +126,22 @@ def test_cli_default_precision_and_errors(cli, tmp_path):
     assert bad.returncode != 0 and "cannot specify both --memory and --blocksize" in bad.stderr
 
 
+def test_cli_ndim_beyond_63(cli, tmp_path):
+    """`--ndim 100` (ncv = 201) and the reference's own maximum on this fileset, 478
+    (flashpca.cpp:623-633): accepted by the guard AND by the solver."""
+    stem = FIXTURES["data_chr1"]
+    _, payload, n, p = load_fixture("data_chr1")
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    for ndim in (100, 478):
+        out = subprocess.run([cli, "--bfile", stem, "--ndim", str(ndim), "--notime", "--precision",
+                              "12", "--suffix", ".%d" % ndim], cwd=tmp_path, capture_output=True,
+                             text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        ev = np.loadtxt(tmp_path / ("eigenvalues.%d" % ndim))
+        assert ev.shape == (ndim,)
+        assert np.abs(ev / O.dense_pca(x, ndim)["d"] - 1).max() < 1e-6
+
+
 def test_nccl_sharded_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:
@@ -203,3 +219,121 @@ def test_cli_streaming_mode_matches_resident(cli, tmp_path):
             assert "streamed from host memory" in out.stdout
         outs[tag] = np.loadtxt(wd / "eigenvalues.txt")
     assert np.abs(outs["str"] / outs["res"] - 1).max() < 1e-9
+
+
+def _script_rmse(a, b):
+    """HapMap3/test_pca.R:156-160: sign-invariant per-column criterion of the reference script."""
+    r = [min(np.mean(a[:, m] - b[:, m]) ** 2, np.mean(a[:, m] + b[:, m]) ** 2)
+         for m in range(a.shape[1])]
+    return float(np.sqrt(np.sum(r)))
+
+
+def test_reference_end_to_end_script(cli, tmp_path):
+    """HapMap3/test_pca.R:40-246 with numpy's dense SVD in the place of R's svd()/RSpectra:
+    PCA of HM3_thinned_autosomal_overlap (--ndim 10 --tol 1e-6 --outload --outmeansd --precision 20),
+    --project onto the same data, onto the 1000 Genomes set (N = 1092, no missing genotypes) and with
+    --inmaf, then --check; FID/IID and SNP/allele order exact, everything else at err.tol = 1e-6."""
+    import re
+    from conftest import GOLDEN
+    hm3 = os.path.join(GOLDEN, "hm3_overlap", "HM3_thinned_autosomal_overlap")
+    kg1 = os.path.join(GOLDEN, "kg1_overlap",
+                       "1kg.ref.phase1_release_v3.20101123_thinned_autosomal_overlap")
+    k, tol, err_tol = 10, 1e-6, 1e-6
+
+    def run(*args):
+        out = subprocess.run([cli, *args], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        return out.stdout
+
+    # ---- the script's R side, in numpy (scale2, svd)
+    n1 = O.count_lines(hm3 + ".fam")
+    pay1, _, p = O.read_bed_payload(hm3 + ".bed", n1)
+    d1 = O.dosage_matrix(O.dense_codes(pay1, n1, p))
+    maf = np.nanmean(d1, axis=0) / 2
+    center, scale = 2 * maf, np.sqrt(2 * maf * (1 - maf))
+    x = (d1 - center) / scale
+    x[np.isnan(x)] = 0.0
+    x /= np.sqrt(p)
+    u, s, vt = np.linalg.svd(x, full_matrices=False)
+    u, s, v = u[:, :k], s[:k], vt[:k].T
+    fam = [ln.split() for ln in open(hm3 + ".fam")]
+    bim = [ln.split() for ln in open(hm3 + ".bim")]
+
+    # ---- the script's command lines
+    run("--bfile", hm3, "--ndim", str(k), "--tol", str(tol), "--outload", "loadings.txt",
+        "--outmeansd", "meansd.txt", "--precision", "20")
+    run("--bfile", hm3, "--project", "--inmeansd", "meansd.txt", "--outproj", "projections.txt",
+        "--inload", "loadings.txt", "-v", "--precision", "20")
+    run("--bfile", kg1, "--project", "--inmeansd", "meansd.txt", "--outproj", "projections.1kg.txt",
+        "--inload", "loadings.txt", "-v", "--precision", "20")
+    chk = run("--bfile", hm3, "--check", "--outval", "eigenvalues.txt", "--outvec",
+              "eigenvectors.txt", "-v", "--precision", "20", "--notime")
+
+    hdr, ids, evec = _read_table(tmp_path / "eigenvectors.txt")
+    assert [r[0] for r in ids] == [f[0] for f in fam] and [r[1] for r in ids] == [f[1] for f in fam]
+    ev = np.loadtxt(tmp_path / "eigenvalues.txt")
+    _, ids, pcs = _read_table(tmp_path / "pcs.txt")
+    assert [r[0] for r in ids] == [f[0] for f in fam] and [r[1] for r in ids] == [f[1] for f in fam]
+    pve = np.loadtxt(tmp_path / "pve.txt")
+    _, sid, msd = _read_table(tmp_path / "meansd.txt")
+    assert [r[0] for r in sid] == [b[1] for b in bim] and [r[1] for r in sid] == [b[4] for b in bim]
+    _, sid, load = _read_table(tmp_path / "loadings.txt")
+    assert [r[0] for r in sid] == [b[1] for b in bim] and [r[1] for r in sid] == [b[4] for b in bim]
+    _, ids, proj = _read_table(tmp_path / "projections.txt")
+    assert [r[0] for r in ids] == [f[0] for f in fam] and [r[1] for r in ids] == [f[1] for f in fam]
+    _, ids1kg, proj1kg = _read_table(tmp_path / "projections.1kg.txt")
+    fam2 = [ln.split() for ln in open(kg1 + ".fam")]
+    assert [r[0] for r in ids1kg] == [f[0] for f in fam2] and [r[1] for r in ids1kg] == [f[1] for f in fam2]
+
+    # scaling (test_pca.R:123-139), eigenvalues (:143-150), pve (:184-192)
+    assert np.sqrt(np.mean((msd[:, 0] - center) ** 2)) < err_tol
+    assert np.sqrt(np.mean((msd[:, 1] - scale) ** 2)) < err_tol
+    assert np.sqrt(np.mean((ev - s ** 2) ** 2)) < err_tol
+    assert np.sqrt(np.mean((pve - s ** 2 / (x ** 2).sum()) ** 2)) < err_tol
+    # eigenvectors, PCs, loadings, projection = PCs (:154-228): the script's criterion and a
+    # stricter element-wise one (tol 1e-6 solve: vector error ~ residual / gap)
+    xv = x @ v
+    for got, want, scale_ in ((evec, u, 1.0), (pcs, xv, np.abs(xv).max()), (load, v, 1.0),
+                              (proj, xv, np.abs(xv).max())):
+        assert _script_rmse(got, want) < err_tol
+        assert np.abs(O.sign_align(got, want) - want).max() < 2e-5 * scale_
+    # 1KG projected onto the HM3 PCA (:111-114, 232-245)
+    n2 = O.count_lines(kg1 + ".fam")
+    pay2, _, p2 = O.read_bed_payload(kg1 + ".bed", n2)
+    assert (n2, p2) == (1092, p)
+    d2 = O.dosage_matrix(O.dense_codes(pay2, n2, p2))
+    assert not np.isnan(d2).any()
+    want1kg = ((d2 - center) / scale) @ v / np.sqrt(p)
+    assert _script_rmse(proj1kg, want1kg) < err_tol
+    assert np.abs(O.sign_align(proj1kg, want1kg) - want1kg).max() < 2e-5 * np.abs(want1kg).max()
+    # --check (:70-76, 107-110, 249-250): printed sums of squared errors vs the dense formula
+    rows = [re.split(r",| ", ln) for ln in chk.splitlines() if "eval" in ln]
+    assert len(rows) == k
+    sse_obs = np.array([float(r[6]) for r in rows])
+    assert np.allclose([float(r[1]) for r in rows], ev, rtol=1e-12)
+    sse_exp = ((x @ (x.T @ evec) - evec * ev[None, :]) ** 2).sum(axis=0)
+    assert ((sse_obs - sse_exp) ** 2 < err_tol).all()
+    assert np.sqrt(sse_obs.sum() / (n1 * k)) < 1e-4       # README.md:207: mse < 1e-8
+
+    # --inmaf (:62-67).  The script writes a 2-column maf.txt, which read_MAF (data.cpp:419-496)
+    # rejects: it wants PLINK .frq rows (CHR SNP A1 A2 MAF NCHROBS), and maf2meansd
+    # (randompca.cpp:745-751) uses sd = 2 p (1 - p) without the square root.
+    with open(tmp_path / "maf.txt", "w") as f:
+        f.write("SNP MAF\n")
+        for b, m in zip(bim, maf):
+            f.write("%s %.20g\n" % (b[1], m))
+    bad = subprocess.run([cli, "--bfile", hm3, "--project", "--inmaf", "maf.txt", "--outproj",
+                          "projections.maf.txt", "--inload", "loadings.txt"], cwd=tmp_path,
+                         capture_output=True, text=True)
+    assert bad.returncode != 0 and "inconsistent number of columns" in bad.stderr
+    with open(tmp_path / "hm3.frq", "w") as f:
+        f.write(" CHR SNP A1 A2 MAF NCHROBS\n")
+        for b, m in zip(bim, maf):
+            f.write(" %s %s %s %s %.20g %d\n" % (b[0], b[1], b[4], b[5], m, 2 * n1))
+    run("--bfile", hm3, "--project", "--inmaf", "hm3.frq", "--outproj", "projections.maf.txt",
+        "--inload", "loadings.txt", "--precision", "20")
+    _, _, projmaf = _read_table(tmp_path / "projections.maf.txt")
+    xm = (d1 - 2 * maf) / (2 * maf * (1 - maf))
+    xm[np.isnan(xm)] = 0.0
+    wantmaf = xm @ load / np.sqrt(p)
+    assert np.abs(projmaf - wantmaf).max() < 1e-9 * np.abs(wantmaf).max()

@@ -304,6 +304,55 @@ def test_pca_vs_dense_eigh(native_lib, name, ndim):
     assert np.abs(r3.Px - r2.Px).max() < 1e-5 * np.abs(r2.Px).max()
 
 
+@pytest.mark.parametrize("name,ndim", [("hapmap3", 100), ("data_chr1", 200), ("data_chr1", 478)])
+def test_pca_large_ndim(native_lib, name, ndim):
+    """ndim up to the reference's own limit (min(N, P) - 1) / 2 (flashpca.cpp:623-633; 478 on the
+    R fixture, test_pca.R:5 uses 50): ncv = 2 ndim + 1 goes up to N = 957 here.  Eigenvalues and pve
+    vs dense eigh at the reference's default tol, --check mse on the solver's own eigenpairs."""
+    _, payload, n, p = load_fixture(name)
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, ndim)
+    op = _mk(payload, n, p)
+    res = op.pca(ndim, 2 * ndim + 1, 500, 1e-6)
+    assert res["nconv"] == ndim
+    d = res["values"] / p
+    assert np.abs(d / ref["d"] - 1).max() < 1e-6
+    err = op.pca_residual(ndim, float(p))
+    assert err.sum() / (n * ndim) < 1e-8
+    u = res["vectors"]
+    assert np.abs(u.T @ u - np.eye(ndim)).max() < 1e-10
+    # the device check equals the host formula of randompca.cpp:663-703
+    y = op.perform_op_mat(u) / p
+    host_err = ((y - u * d[None, :]) ** 2).sum(axis=0)
+    assert np.allclose(err, host_err, rtol=1e-6, atol=1e-18)
+    op.close()
+
+
+def test_solve_parity_at_10k_x_100k(native_lib, monkeypatch):
+    """BASELINE configs[1] (synthetic 10,000 x 100,000, k = 20): the full GPU solve against the CPU
+    oracle's solve (C restatement of the operator under the oracle's Spectra restatement) on the
+    same matrix: eigenvalues 1e-6 relative at the reference's tol, eigenvectors sign-aligned at a
+    tighter tol (vector error ~ residual / gap), --check mse < 1e-8 (README.md:207)."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    from flashpca_b200.synth import SynthSpec
+    n, p, k = 10000, 100000, 20
+    s = SynthSpec(n, p)
+    op = s.create_operator()
+    payload = op.bed_payload()                      # the matrix the GPU holds, fed to the oracle
+    got = op.pca(k, 2 * k + 1, 500, 1e-6)
+    assert got["nconv"] == k
+    err = op.pca_residual(k, float(p))
+    assert err.sum() / (n * k) < 1e-8
+    # one CPU solve, converged tightly (about 100-150 oracle ops of 1e9 genotypes each)
+    want = O.oracle_pca(payload, n, p, k, tol=1e-8, block_size=4096)
+    assert np.abs(got["values"] / p / want["d"] - 1).max() < 1e-6
+    tight = op.pca(k, 2 * k + 1, 500, 1e-8)
+    u = O.sign_align(tight["vectors"], want["U"])
+    assert np.abs(u - want["U"]).max() < 1e-6
+    assert np.abs(tight["values"] / p / want["d"] - 1).max() < 1e-9
+    op.close()
+
+
 def test_gpu_solver_vs_oracle_solver_same_tol(native_lib, path):
     """Device IRLM and the oracle's Spectra restatement, same start vector and
     tolerance, on the C oracle operator vs the CUDA operator."""

@@ -191,3 +191,12 @@ def test_standardise_matrix_restatement(method):
     if method == 3:   # the matrix path and the bed path standardise identically
         xb, _ = O.dense_standardise(O.dense_codes(payload, n, p)[:, :200])
         assert np.allclose(s, xb, rtol=1e-13, atol=1e-13)
+
+
+def test_host_synth_generator_matches_numpy_generator():
+    """The C generator bench.py uses for the CPU baseline's input equals synth.py bit for bit
+    (which the device generator equals too, test_gpu_parity.py)."""
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(1003, 300, seed=5)
+    assert np.array_equal(O.synth_packed_bed(s, 17, 211), s.packed_bed(17, 211))
+    assert np.array_equal(O.synth_packed_bed(s, 0, 300), s.packed_bed())
