@@ -28,6 +28,7 @@
 #include <chrono>
 #include <cmath>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <stdlib.h>
@@ -44,6 +45,9 @@
 namespace {
 
 thread_local std::string g_err;
+// fpb_create_streaming stages every slab straight into one of its two slab buffers: when set,
+// alloc_common uses this allocation for d_gs instead of a fresh one (the caller detaches it again)
+thread_local uint8_t* g_borrow_gs = nullptr;
 
 struct Tiling {
   int W = 1;
@@ -108,6 +112,7 @@ struct fpb_handle {
   double* d_t = nullptr;
   double4* d_coef = nullptr;
   double* d_c0 = nullptr;
+  double* d_gpart = nullptr;  // generic path: fixed-order partials (allocated on first use)
   Tiling tl;
   // in-memory matrix path (fpb_create_dense): N x P doubles, already standardised
   bool dense = false;
@@ -187,6 +192,9 @@ struct fpb_handle {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   double* d_ytmp = nullptr;
   bool borrowed = false;                   // kid: streams and d_gs belong to the parent
+  bool shared_scratch = false;             // kid: per-op scratch (slices, partials, a/corr, gather sums)
+                                           // belongs to the parent, one set sized for the largest slab
+  std::vector<char> kid_host_pinned;       // parent: kid_host[b] came from cudaMallocHost (else malloc)
   // pinned bounce buffers for large device -> pageable-host downloads (fpb_pca eigenvectors)
   unsigned char* h_bounce[2] = {nullptr, nullptr};
   cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
@@ -200,6 +208,14 @@ struct fpb_handle {
   uint64_t launches = 0;
   std::vector<float> op_ms;
   std::vector<double> last_evals;  // Ritz values of the last fpb_pca call (fpb_pca_residual)
+  // CUDA graphs of the single-vector perform_op, one per (x, y) pointer pair: the ~14 launches of
+  // an op (two streams, one ncclAllReduce when sharded) replay as one graph launch
+  struct OpGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;
+  };
+  std::unordered_map<uint64_t, OpGraph> op_graphs;
+  bool graphs_ok = true;           // cleared when a capture fails: plain launches from then on
   fpb::Irlm* solver = nullptr;  // Lanczos workspace, kept between fpb_pca calls
   // fpb_time_perform_op: events bracketing the two contraction-kernel launches
   bool time_gemv = false;
@@ -290,7 +306,8 @@ int alloc_common(fpb_handle* h, uint64_t n, uint64_t nsnps, int stand_method, in
   h->pitch_s = (h->np + 63) / 64 * 64;
   h->pitch_i = ((nsnps + 3) / 4 + 63) / 64 * 64;
   h->stand_method = stand_method;
-  FPB_CUDA(h, cudaMalloc(&h->d_gs, h->pitch_s * nsnps));
+  if (g_borrow_gs) h->d_gs = g_borrow_gs;
+  else FPB_CUDA(h, cudaMalloc(&h->d_gs, h->pitch_s * nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_lut, sizeof(double4) * nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_scale, sizeof(double2) * nsnps));
   FPB_CUDA(h, cudaMalloc(&h->d_meansd, sizeof(double) * 2 * nsnps));
@@ -734,37 +751,56 @@ int ensure_staging(fpb_handle* h, size_t in_elems, size_t out_elems) {
 
 // ------------------------------ generic FP64 path --------------------------
 
+// per-(chunk, warp) partials of t and per-split partials of y: summed in a fixed order, so the
+// generic path is as bit-reproducible as the tensor path
+int ensure_generic_scratch(fpb_handle* h) {
+  if (h->d_gpart) return 0;
+  const Tiling& t = h->tl;
+  const size_t rows_t = (size_t)t.chunks * (t.block / 32);
+  const size_t need = std::max(rows_t * h->nsnps, (size_t)t.splits * h->n);
+  FPB_CUDA(h, cudaMalloc(&h->d_gpart, sizeof(double) * need));
+  return 0;
+}
+
 void generic_crossprod(fpb_handle* h, const double* d_x, double* d_t) {
   const Tiling& t = h->tl;
-  cudaMemsetAsync(d_t, 0, sizeof(double) * h->nsnps, h->stream);
+  if (ensure_generic_scratch(h)) return;
   dim3 grid(t.chunks, t.splits);
   if (t.W == 1)
     fpb::k_crossprod<1><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
                                                           (uint32_t)h->nsnps, t.snps_per_split,
-                                                          d_x, h->d_lut, d_t);
+                                                          d_x, h->d_lut, h->d_gpart);
   else
     fpb::k_crossprod<2><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
                                                           (uint32_t)h->nsnps, t.snps_per_split,
-                                                          d_x, h->d_lut, d_t);
-  h->launches++;
+                                                          d_x, h->d_lut, h->d_gpart);
+  fpb::k_sum_rows<<<(uint32_t)((h->nsnps + 255) / 256), 256, 0, h->stream>>>(
+      h->d_gpart, t.chunks * (t.block / 32), h->nsnps, d_t);
+  h->launches += 2;
 }
 
 void generic_prod(fpb_handle* h, const double* d_v, double* d_y) {
   const Tiling& t = h->tl;
+  if (ensure_generic_scratch(h)) return;
   uint32_t gb = (uint32_t)((h->nsnps + 255) / 256);
   fpb::k_prod_coef<<<gb, 256, 0, h->stream>>>(h->d_lut, d_v, (uint32_t)h->nsnps, h->d_coef);
   fpb::k_sum_a0<<<1, 1024, 0, h->stream>>>(h->d_coef, (uint32_t)h->nsnps, h->d_c0);
-  if (t.splits > 1) cudaMemsetAsync(d_y, 0, sizeof(double) * h->n, h->stream);
+  double* dst = t.splits > 1 ? h->d_gpart : d_y;
   dim3 grid(t.chunks, t.splits);
   if (t.W == 1)
     fpb::k_prod<1><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
                                                      (uint32_t)h->nsnps, t.snps_per_split,
-                                                     h->d_coef, h->d_c0, d_y);
+                                                     h->d_coef, h->d_c0, dst);
   else
     fpb::k_prod<2><<<grid, t.block, 0, h->stream>>>(h->d_gs, h->pitch_s, h->n,
                                                      (uint32_t)h->nsnps, t.snps_per_split,
-                                                     h->d_coef, h->d_c0, d_y);
+                                                     h->d_coef, h->d_c0, dst);
   h->launches += 3;
+  if (t.splits > 1) {
+    fpb::k_sum_rows<<<(uint32_t)((h->n + 255) / 256), 256, 0, h->stream>>>(h->d_gpart, t.splits,
+                                                                          h->n, d_y);
+    h->launches++;
+  }
 }
 
 // ------------------------------ tensor path --------------------------------
@@ -1131,6 +1167,7 @@ int fpb_create_from_file(fpb_handle** out, const char* bed_path, uint64_t n, uin
   if (!rc) rc = finish_create(h, preloaded_meansd);
   if (rc) {
     g_err = h->err;
+    if (g_borrow_gs) h->d_gs = nullptr;  // the slab buffer belongs to the streaming parent
     fpb_destroy(h);
     return 1;
   }
@@ -1252,10 +1289,18 @@ void fpb_destroy(fpb_handle* h) {
       kid->side = nullptr;
       kid->d_gs = nullptr;
     }
+    if (kid->shared_scratch) {  // freed once, below, through this handle's own fields
+      kid->d_slices = nullptr;
+      kid->d_part = kid->d_a = kid->d_corr = kid->d_pmax = kid->d_psum = kid->d_mx = kid->d_mc = nullptr;
+      kid->d_sc = nullptr;
+    }
     fpb_destroy(kid);
   }
-  for (uint8_t* p : h->kid_host)
-    if (p) cudaFreeHost(p);
+  for (size_t b = 0; b < h->kid_host.size(); b++)
+    if (h->kid_host[b]) {
+      if (b < h->kid_host_pinned.size() && !h->kid_host_pinned[b]) free(h->kid_host[b]);
+      else cudaFreeHost(h->kid_host[b]);
+    }
   for (int i = 0; i < 2; i++) {
     cudaFree(h->sbuf[i]);
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -1285,6 +1330,8 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_sc);
   cudaFree(h->d_mx);
   cudaFree(h->d_mc);
+  for (auto& kv : h->op_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   free_umma(h);
   cudaFree(h->L1.slices);
   cudaFree(h->L1.part);
@@ -1312,6 +1359,7 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_t);
   cudaFree(h->d_coef);
   cudaFree(h->d_c0);
+  cudaFree(h->d_gpart);
   cudaFree(h->d_in);
   cudaFree(h->d_out);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1444,8 +1492,58 @@ int fpb_perform_op_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, doubl
   return allreduce(h, d_y, (size_t)h->n * k);
 }
 
+namespace {
+bool graph_capable(const fpb_handle* h) {
+  static const bool off = getenv("FPB_GRAPH") && atoi(getenv("FPB_GRAPH")) == 0;
+  return !off && h->graphs_ok && h->kids.empty() && !h->dense && h->use_imma && !h->use_fused &&
+         !h->time_gemv;
+}
+}  // namespace
+
+// y = X X' x, device pointers.  After one plain call per (x, y) pair (which also makes every lazily
+// allocated buffer exist) the op is captured once and replayed as a CUDA graph.
 int fpb_perform_op_dev(fpb_handle* h, const double* d_x, double* d_y) {
-  return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+  if (!h || !d_x || !d_y) FPB_FAIL(h, "null argument");
+  if (!graph_capable(h)) return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  const uint64_t key = (uint64_t)(uintptr_t)d_x * 0x9E3779B97F4A7C15ull ^ (uint64_t)(uintptr_t)d_y;
+  auto it = h->op_graphs.find(key);
+  if (it == h->op_graphs.end()) {
+    if (h->op_graphs.size() >= 256) {  // bounded cache
+      for (auto& kv : h->op_graphs) cudaGraphExecDestroy(kv.second.exec);
+      h->op_graphs.clear();
+    }
+    h->op_graphs[key] = fpb_handle::OpGraph();  // seen once: capture on the next call
+    return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+  }
+  if (!it->second.exec) {
+    const uint64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      h->graphs_ok = false;
+      return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+    }
+    const int rc = fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc || ce != cudaSuccess || !graph ||
+        cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      h->graphs_ok = false;
+      h->launches = l0;
+      h->op_graphs.erase(key);
+      return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+    }
+    cudaGraphDestroy(graph);
+    it->second.exec = exec;
+    it->second.launches = h->launches - l0;
+    h->launches = l0;
+  }
+  FPB_CUDA(h, cudaGraphLaunch(it->second.exec, h->stream));
+  h->launches += it->second.launches;
+  return 0;
 }
 
 // ------------------------------ host-pointer ops ---------------------------
@@ -1458,7 +1556,11 @@ static int host_op(fpb_handle* h, const double* in, uint32_t k, double* out, uin
   if (ensure_staging(h, (size_t)in_rows * k, (size_t)out_rows * k)) return 1;
   FPB_CUDA(h, cudaMemcpyAsync(h->d_in, in, sizeof(double) * in_rows * k, cudaMemcpyHostToDevice,
                               h->stream));
-  if (dev_fn(h, h->d_in, k, h->d_out)) return 1;
+  if (k == 1 && dev_fn == fpb_perform_op_multi_dev) {  // graph-replayed single-vector op
+    if (fpb_perform_op_dev(h, h->d_in, h->d_out)) return 1;
+  } else if (dev_fn(h, h->d_in, k, h->d_out)) {
+    return 1;
+  }
   FPB_CUDA(h, cudaMemcpyAsync(out, h->d_out, sizeof(double) * out_rows * k,
                               cudaMemcpyDeviceToHost, h->stream));
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -89,33 +89,49 @@ k_dense_standardise(double* __restrict__ X, uint64_t n, uint32_t p, int method,
   }
 }
 
-// t_j = sum_i X_ij x_i, one block per column, fixed order
+// t_j = sum_i X_ij x_i, one block per column, fixed order.  Four independent 8-byte loads of the
+// column per thread and iteration (8 KB of the column in flight per block) keep the 8 N P byte
+// stream of svdwide.cpp:10 (`mat.transpose() * x`) at HBM speed.
 __global__ void __launch_bounds__(256)
 k_dense_gemv_t(const double* __restrict__ X, uint64_t n, const double* __restrict__ x,
                double* __restrict__ t) {
   __shared__ double sh[8][3];
   const double* col = X + (uint64_t)blockIdx.x * n;
-  double s = 0.0, d0 = 0.0, d1 = 0.0;
-  for (uint64_t i = threadIdx.x; i < n; i += 256) s += col[i] * x[i];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  uint64_t i = threadIdx.x;
+  for (; i + 768 < n; i += 1024) {
+    const double c0 = col[i], c1 = col[i + 256], c2 = col[i + 512], c3 = col[i + 768];
+    s0 += c0 * x[i];
+    s1 += c1 * x[i + 256];
+    s2 += c2 * x[i + 512];
+    s3 += c3 * x[i + 768];
+  }
+  for (; i < n; i += 256) s0 += col[i] * x[i];
+  double s = (s0 + s1) + (s2 + s3), d0 = 0.0, d1 = 0.0;
   block_sum3(s, d0, d1, sh);
   if (threadIdx.x == 0) t[blockIdx.x] = s;
 }
 
-// partial[split * n + i] = sum_{j in split} X_ij t_j   (thread per row, coalesced columns)
+// partial[split * n + i] = sum_{j in split} X_ij t_j   (thread per row, coalesced columns, four
+// columns in flight per thread)
 __global__ void __launch_bounds__(256)
 k_dense_gemv_n(const double* __restrict__ X, uint64_t n, uint32_t p, uint32_t cols_per_split,
                const double* __restrict__ t, double* __restrict__ partial) {
   uint64_t i = blockIdx.x * (uint64_t)256 + threadIdx.x;
   if (i >= n) return;
   uint32_t j0 = blockIdx.y * cols_per_split, j1 = min(p, j0 + cols_per_split);
-  double s0 = 0.0, s1 = 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   uint32_t j = j0;
-  for (; j + 1 < j1; j += 2) {
-    s0 += X[i + (uint64_t)j * n] * t[j];
-    s1 += X[i + (uint64_t)(j + 1) * n] * t[j + 1];
+  for (; j + 3 < j1; j += 4) {
+    const double c0 = X[i + (uint64_t)j * n], c1 = X[i + (uint64_t)(j + 1) * n],
+                 c2 = X[i + (uint64_t)(j + 2) * n], c3 = X[i + (uint64_t)(j + 3) * n];
+    s0 += c0 * t[j];
+    s1 += c1 * t[j + 1];
+    s2 += c2 * t[j + 2];
+    s3 += c3 * t[j + 3];
   }
-  if (j < j1) s0 += X[i + (uint64_t)j * n] * t[j];
-  partial[(uint64_t)blockIdx.y * n + i] = s0 + s1;
+  for (; j < j1; j++) s0 += X[i + (uint64_t)j * n] * t[j];
+  partial[(uint64_t)blockIdx.y * n + i] = (s0 + s1) + (s2 + s3);
 }
 
 __global__ void k_sum_splits(const double* __restrict__ partial, uint32_t nsplits, uint64_t n,

@@ -61,18 +61,41 @@ int fpb_create_streaming(fpb_handle** out, const char* bed_path, uint64_t n, uin
         kid_msd = msd.data();
       }
       fpb_handle* kid = nullptr;
-      if (fpb_create_from_file(&kid, bed_path, n, snp_begin + off, cnt, stand_method, kid_msd,
-                               device))
-        FPB_FAIL(h, g_err);
+      // the slab is staged (read, recoded, statistics, missing-genotype lists) inside slab buffer 0:
+      // no third slab-sized allocation next to the two buffers
+      g_borrow_gs = h->sbuf[0];
+      const int crc = fpb_create_from_file(&kid, bed_path, n, snp_begin + off, cnt, stand_method,
+                                           kid_msd, device);
+      g_borrow_gs = nullptr;
+      if (crc) FPB_FAIL(h, g_err);
       h->kids.push_back(kid);
       h->kid_off.push_back(off);
       h->kid_host.push_back(nullptr);
-      // the recoded genotypes leave HBM: pinned host memory is their home from now on
-      FPB_CUDA(h, cudaMallocHost(&h->kid_host.back(), kid->pitch_s * cnt));
+      h->kid_host_pinned.push_back(1);
+      kid->borrowed = true;  // from here on fpb_destroy(kid) must not free the slab buffer
+      // the recoded genotypes leave HBM: host memory is their home from now on.  Pinned when the
+      // host allows it (the copy engine then overlaps the kernels); a bed that cannot be pinned
+      // (larger than the lockable memory) falls back to pageable memory, slab by slab.
+      if (cudaMallocHost(&h->kid_host.back(), kid->pitch_s * cnt) != cudaSuccess) {
+        cudaGetLastError();
+        h->kid_host.back() = (uint8_t*)malloc(kid->pitch_s * cnt);
+        h->kid_host_pinned.back() = 0;
+        if (!h->kid_host.back()) FPB_FAIL(h, "out of host memory for the streamed genotypes");
+      }
       FPB_CUDA(h, cudaMemcpy(h->kid_host.back(), kid->d_gs, kid->pitch_s * cnt,
                              cudaMemcpyDeviceToHost));
-      cudaFree(kid->d_gs);
       kid->d_gs = nullptr;
+      // per-op scratch: one set for all slabs (they run one after the other on one stream), sized
+      // for the largest; freed here so that staging the next slab does not stack allocations
+      if (kid->use_imma) {
+        cudaFree(kid->d_slices); cudaFree(kid->d_part); cudaFree(kid->d_a); cudaFree(kid->d_corr);
+        cudaFree(kid->d_pmax); cudaFree(kid->d_psum); cudaFree(kid->d_sc); cudaFree(kid->d_mx);
+        cudaFree(kid->d_mc);
+        kid->d_slices = nullptr;
+        kid->d_part = kid->d_a = kid->d_corr = kid->d_pmax = kid->d_psum = kid->d_mx = kid->d_mc = nullptr;
+        kid->d_sc = nullptr;
+        kid->shared_scratch = true;
+      }
       if (kid->use_imma && kid->use_tma)
         for (int i = 0; i < 2; i++) {
           if (make_tensor_map(kid, h->sbuf[i], kid->pitch_s, cnt, &kid->tm_s_alt[i]) ||
@@ -83,13 +106,51 @@ int fpb_create_streaming(fpb_handle** out, const char* bed_path, uint64_t n, uin
       cudaStreamDestroy(kid->side);
       kid->stream = h->stream;
       kid->side = h->side;
-      kid->borrowed = true;
       h->trace += kid->trace;  // slab order, like the block loop of svdwide.cpp:44-61
       h->launches += kid->launches;
       kid->launches = 0;
     }
+    // the shared per-op scratch, held in this (parent) handle's own fields
+    size_t slice_b = 0, part_e = 0, snps_e = 0, parts_e = 0, mx_e = 0, mc_e = 0;
+    for (fpb_handle* kid : h->kids)
+      if (kid->shared_scratch) {
+        slice_b = std::max(slice_b, kid->slice_bytes);
+        part_e = std::max(part_e, kid->part_elems);
+        snps_e = std::max<size_t>(snps_e, kid->nsnps);
+        parts_e = std::max(parts_e, kid->max_parts);
+        if (kid->nmissing) {
+          mx_e = std::max<size_t>(mx_e, (size_t)kid->nsnps * kid->gtiles_s);
+          mc_e = std::max<size_t>(mc_e, (size_t)kid->n * kid->gtiles_i);
+        }
+      }
+    if (slice_b) {
+      FPB_CUDA(h, cudaMalloc(&h->d_slices, slice_b));
+      FPB_CUDA(h, cudaMalloc(&h->d_part, sizeof(double) * part_e));
+      FPB_CUDA(h, cudaMalloc(&h->d_a, sizeof(double) * snps_e));
+      FPB_CUDA(h, cudaMalloc(&h->d_corr, sizeof(double) * snps_e));
+      FPB_CUDA(h, cudaMalloc(&h->d_pmax, sizeof(double) * parts_e));
+      FPB_CUDA(h, cudaMalloc(&h->d_psum, sizeof(double) * parts_e));
+      FPB_CUDA(h, cudaMalloc(&h->d_sc, sizeof(fpb::VecScale) * 2));
+      if (mx_e) FPB_CUDA(h, cudaMalloc(&h->d_mx, sizeof(double) * mx_e));
+      if (mc_e) FPB_CUDA(h, cudaMalloc(&h->d_mc, sizeof(double) * mc_e));
+      for (fpb_handle* kid : h->kids)
+        if (kid->shared_scratch) {
+          kid->d_slices = h->d_slices;
+          kid->d_part = h->d_part;
+          kid->d_a = h->d_a;
+          kid->d_corr = h->d_corr;
+          kid->d_pmax = h->d_pmax;
+          kid->d_psum = h->d_psum;
+          kid->d_sc = h->d_sc;
+          kid->d_mx = h->d_mx;
+          kid->d_mc = h->d_mc;
+        }
+    }
+    h->sbuf_holds[0] = (long long)h->kids.size() - 1;  // the last slab staged is still in buffer 0 ...
+    if (((h->kids.size() - 1) & 1) != 0) h->sbuf_holds[0] = -1;  // ... usable only if that is its buffer
     return 0;
   }();
+  g_borrow_gs = nullptr;
   if (rc) {
     g_err = h->err;
     fpb_destroy(h);

@@ -287,13 +287,14 @@ __global__ void k_keys_to_csr(const uint64_t* __restrict__ keys, uint64_t nnz,
 // bit]; a rare slow path adds M = sum x_i [missing].  With S_e = sum of x over
 // genotypes with code e:  S1 = L - M, S2 = H - M, S0 = Stot - L - H + M and
 //   t_j partial = l0*S0 + l1*S1 + l2*S2,
-// warp-reduced by shuffles and added to t[j] with one FP64 atomic per warp.
+// warp-reduced by shuffles and written to part[(chunk, warp)][j]; k_sum_rows adds the
+// (chunk, warp) partials of a SNP in a fixed order (no atomics: bit-reproducible).
 // ---------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(256)
 k_crossprod(const uint8_t* __restrict__ gs, uint64_t pitch, uint64_t n, uint32_t nsnps,
             uint32_t snps_per_split, const double* __restrict__ x,
-            const double4* __restrict__ lut, double* __restrict__ t) {
+            const double4* __restrict__ lut, double* __restrict__ part) {
   const uint32_t words_per_row = (uint32_t)(pitch / 4);
   const uint32_t widx = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const bool active = widx < words_per_row;
@@ -342,8 +343,19 @@ k_crossprod(const uint8_t* __restrict__ gs, uint64_t pitch, uint64_t n, uint32_t
     const double4 l = lut[j];
     double tj = l.x * (stot - ls - hs + ms) + l.y * (ls - ms) + l.z * (hs - ms);
     tj = warp_sum(tj);
-    if ((threadIdx.x & 31) == 0) atomicAdd(t + j, tj);
+    if ((threadIdx.x & 31) == 0)
+      part[((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * nsnps + j] = tj;
   }
+}
+
+// out[c] = sum_r part[r * ncols + c], r ascending (fixed order)
+__global__ void k_sum_rows(const double* __restrict__ part, uint32_t nrows, uint64_t ncols,
+                           double* __restrict__ out) {
+  uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (uint32_t r = 0; r < nrows; r++) s += part[(uint64_t)r * ncols + c];
+  out[c] = s;
 }
 
 // Per-SNP coefficients for the generic prod:  with a_e = l_e * v_j,
@@ -380,7 +392,7 @@ template <int W>
 __global__ void __launch_bounds__(256)
 k_prod(const uint8_t* __restrict__ gs, uint64_t pitch, uint64_t n, uint32_t nsnps,
        uint32_t snps_per_split, const double4* __restrict__ coef,
-       const double* __restrict__ c0, double* __restrict__ y) {
+       const double* __restrict__ c0, double* __restrict__ y /* [split][n] when gridDim.y > 1 */) {
   const uint32_t words_per_row = (uint32_t)(pitch / 4);
   const uint32_t widx = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   if (widx >= words_per_row) return;
@@ -421,10 +433,7 @@ k_prod(const uint8_t* __restrict__ gs, uint64_t pitch, uint64_t n, uint32_t nsnp
 #pragma unroll
   for (int k = 0; k < 16 * W; k++) {
     uint64_t i = (uint64_t)widx * 16 + k;
-    if (i < n) {
-      if (gridDim.y == 1) y[i] = acc[k];
-      else atomicAdd(y + i, acc[k]);
-    }
+    if (i < n) y[(uint64_t)blockIdx.y * n + i] = acc[k];  // per-split partials, summed in split order
   }
 }
 

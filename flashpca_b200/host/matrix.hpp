@@ -2,6 +2,7 @@
 // Eigen::MatrixXd / VectorXd members of upstream's Data and RandomPCA; Eigen is
 // not a dependency of this host layer).
 #pragma once
+#include <algorithm>
 #include <cstddef>
 #include <vector>
 
@@ -12,6 +13,11 @@ struct Matrix {
   std::vector<double> v;
   Matrix() = default;
   Matrix(size_t r, size_t c, double init = 0.0) : nrow(r), ncol(c), v(r * c, init) {}
+  static Matrix from_column_major(const double* src, size_t r, size_t c) {
+    Matrix m(r, c);
+    std::copy(src, src + r * c, m.v.begin());
+    return m;
+  }
   double& operator()(size_t r, size_t c) { return v[c * nrow + r]; }
   double operator()(size_t r, size_t c) const { return v[c * nrow + r]; }
   double* data() { return v.data(); }

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 #include <string>
 
@@ -20,6 +21,13 @@
 #include "matrix.hpp"
 
 namespace flashpca {
+
+// owns an fpb_handle from the moment fpb_create* returns, so that a constructor that throws later
+// (C++ does not run the destructor of a partially constructed object) still releases the HBM
+struct HandleDeleter {
+  void operator()(fpb_handle* h) const { fpb_destroy(h); }
+};
+using HandlePtr = std::unique_ptr<fpb_handle, HandleDeleter>;
 
 // Drop-in for upstream class SVDWide (svdwide.h:9-30): the operator of the
 // in-memory path.  Upstream standardises the matrix on the host first
@@ -32,11 +40,20 @@ class SVDWide {
       : n((unsigned int)raw.rows()), p((unsigned int)raw.cols()) {
     verbose = verbose_;
     nops = 1;
-    if (fpb_create_dense(&h, raw.data(), raw.rows(), raw.cols(), stand_method, device))
+    fpb_handle* raw_h = nullptr;
+    if (fpb_create_dense(&raw_h, raw.data(), raw.rows(), raw.cols(), stand_method, device))
       throw std::runtime_error(fpb_last_error(nullptr));
-    fpb_get_trace(h, &trace);
+    owner.reset(raw_h);
+    h = raw_h;
+    if (fpb_get_trace(h, &trace)) throw std::runtime_error(fpb_last_error(h));
   }
-  ~SVDWide() { fpb_destroy(h); }
+#ifdef EIGEN_CORE_H
+  // upstream's own signature (svdwide.h:18): a matrix that standardise() has already processed
+  // (randompca.cpp:127); stand_method 0 = "none" leaves finite values untouched
+  SVDWide(const Eigen::MatrixXd& mat_, bool verbose_ = false)
+      : SVDWide(Matrix::from_column_major(mat_.data(), (size_t)mat_.rows(), (size_t)mat_.cols()), 0,
+                verbose_) {}
+#endif
   SVDWide(const SVDWide&) = delete;
   SVDWide& operator=(const SVDWide&) = delete;
 
@@ -65,6 +82,7 @@ class SVDWide {
   const unsigned int n, p;
   bool verbose;
   unsigned int nops;
+  HandlePtr owner;
   fpb_handle* h = nullptr;
 };
 
@@ -96,20 +114,22 @@ class SVDWideOnline {
       if (bed + bed / 16 > free_b / 10 * 9) slab = std::max<uint64_t>(1, free_b / 4 / np);
     }
     // the standardisation method is Data's, as in data.cpp:279-288
-    const int rc = slab ? fpb_create_streaming(&h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps, slab,
-                                               dat.stand_method_x, pre, device)
-                        : fpb_create_from_file(&h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps,
+    fpb_handle* raw_h = nullptr;
+    const int rc = slab ? fpb_create_streaming(&raw_h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps,
+                                               slab, dat.stand_method_x, pre, device)
+                        : fpb_create_from_file(&raw_h, dat.geno_filename.c_str(), dat.N, 0, dat.nsnps,
                                                dat.stand_method_x, pre, device);
     if (rc) throw std::runtime_error(fpb_last_error(nullptr));
+    owner.reset(raw_h);  // from here on an exception releases the handle and its HBM
+    h = raw_h;
     if (slab && verbose)
       std::cout << "bed streamed from host memory, " << slab << " SNPs per slab" << std::endl;
-    fpb_get_trace(h, &trace);
+    check(fpb_get_trace(h, &trace));
     if (!dat.use_preloaded_maf) {
       dat.X_meansd = Matrix(p, 2);
       check(fpb_get_meansd(h, dat.X_meansd.data()));
     }
   }
-  ~SVDWideOnline() { fpb_destroy(h); }
   SVDWideOnline(const SVDWideOnline&) = delete;
   SVDWideOnline& operator=(const SVDWideOnline&) = delete;
 
@@ -162,9 +182,34 @@ class SVDWideOnline {
     return Y;
   }
 
+#ifdef EIGEN_CORE_H
+  // Upstream's exact signatures (svdwide.h:84-106) for a host that keeps Eigen: include
+  // <Eigen/Core> before this header and the block variants take / return Eigen::MatrixXd.  Eigen's
+  // default storage is column-major, the C ABI's convention, so the data pointers pass straight through.
+  Eigen::MatrixXd perform_op_mat(const Eigen::MatrixXd& x) { return eig(&SVDWideOnline::call_op, x, n, n); }
+  Eigen::MatrixXd perform_op_multi(const Eigen::MatrixXd& x) { return perform_op_mat(x); }
+  Eigen::MatrixXd crossprod2(const Eigen::MatrixXd& x) { return eig(&SVDWideOnline::call_cp, x, n, p); }
+  Eigen::MatrixXd prod3(const Eigen::MatrixXd& x) { return eig(&SVDWideOnline::call_pr, x, p, n); }
+  Eigen::MatrixXd prod2(const Eigen::MatrixXd& x) { return crossprod2(x).transpose(); }
+#endif
+
   fpb_handle* handle() { return h; }
 
  private:
+#ifdef EIGEN_CORE_H
+  int call_op(const double* in, uint32_t k, double* out) { return fpb_perform_op_multi(h, in, k, out); }
+  int call_cp(const double* in, uint32_t k, double* out) { return fpb_crossprod_multi(h, in, k, out); }
+  int call_pr(const double* in, uint32_t k, double* out) { return fpb_prod_multi(h, in, k, out); }
+  Eigen::MatrixXd eig(int (SVDWideOnline::*fn)(const double*, uint32_t, double*), const Eigen::MatrixXd& x,
+                      size_t rows_in, size_t rows_out) {
+    if ((size_t)x.rows() != rows_in)
+      throw std::runtime_error("operator argument has the wrong number of rows");
+    Eigen::MatrixXd Y(rows_out, x.cols());
+    check((this->*fn)(x.data(), (uint32_t)x.cols(), Y.data()));
+    nops++;
+    return Y;
+  }
+#endif
   void check(int rc) {
     if (rc) throw std::runtime_error(fpb_last_error(h));
   }
@@ -177,6 +222,7 @@ class SVDWideOnline {
   bool verbose;
   unsigned int nops;
   unsigned int block_size;
+  HandlePtr owner;
   fpb_handle* h = nullptr;
 };
 

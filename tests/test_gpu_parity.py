@@ -709,8 +709,7 @@ def test_streaming_operator_family(native_lib, path, name, slab):
     assert abs(op.trace - orc.trace) <= 1e-12 * orc.trace
     y = op.perform_op(x)
     assert _relerr(y, y_ref) <= OP_RTOL
-    if path == "imma":                                    # (the generic path sums with atomics)
-        assert np.array_equal(op.perform_op(x), y)        # bit-reproducible
+    assert np.array_equal(op.perform_op(x), y)            # bit-reproducible on both compute paths
     assert _relerr(op.crossprod(x), orc.crossprod(x)) <= OP_RTOL
     assert _relerr(op.prod(v), orc.prod(v)) <= OP_RTOL
     m = rng.standard_normal((n, 2))
@@ -718,6 +717,49 @@ def test_streaming_operator_family(native_lib, path, name, slab):
     with pytest.raises(_lib.FpbError, match="streaming"):
         op.bed_payload()
     op.close()
+
+
+def test_streaming_many_slabs_share_one_scratch_set(native_lib, monkeypatch, tmp_path):
+    """Many slabs at a realistic N: the slabs share ONE set of per-op scratch (digit slices, split
+    partials, gather sums) sized for the largest slab and are staged inside the two slab buffers, so
+    device memory does not grow with the number of slabs -- the case this mode exists for (bed
+    larger than HBM).  Results equal the resident operator's to the FP64 order of the slab sum."""
+    import ctypes
+    from flashpca_b200 import Data, SVDWideOnline
+    from flashpca_b200.synth import SynthSpec
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    s = SynthSpec(60001, 2600, seed=3, missing_rate=0.002)
+    stem = str(tmp_path / "syn")
+    s.write_plink(stem)
+    d = Data()
+    d.read_pheno(stem + ".fam", 6)
+    d.geno_filename = stem + ".bed"
+    d.get_size()
+    fr, tot = ctypes.c_uint64(), ctypes.c_uint64()
+
+    def used():
+        assert native_lib.fpb_device_memory(0, ctypes.byref(fr), ctypes.byref(tot)) == 0
+        return tot.value - fr.value
+
+    base = used()
+    res = SVDWideOnline(d, 0, 3)
+    x = np.random.default_rng(8).standard_normal(s.n)
+    y_res = res.perform_op(x)
+    res.close()
+    few = SVDWideOnline(d, 0, 3, snps_per_slab=1300)     # 2 slabs
+    mem_few = used() - base
+    y_few = few.perform_op(x)
+    few.close()
+    many = SVDWideOnline(d, 0, 3, snps_per_slab=100)     # 26 slabs
+    mem_many = used() - base
+    y_many = many.perform_op(x)
+    assert np.array_equal(many.perform_op(x), y_many)    # bit-reproducible
+    assert _relerr(y_many, y_res) <= 1e-13 and _relerr(y_few, y_res) <= 1e-13
+    got = many.pca(5, 11, 500, 1e-6)
+    assert got["nconv"] == 5
+    many.close()
+    # 13x the slabs, 13x smaller slab buffers: the footprint must shrink, not grow
+    assert mem_many < mem_few, (mem_many, mem_few)
 
 
 def test_streaming_pca_matches_resident(native_lib, monkeypatch):

@@ -35,6 +35,29 @@ def test_product_library_carries_blackwell_native_code(native_lib):
         assert mnemonic in sass, mnemonic
 
 
+def build_eigen_adaptor_check(out_dir):
+    """g++ the Eigen-typed surface of host/svdwide.hpp against the stub <Eigen/Core> of
+    tests/eigen_stub (Eigen is absent from the image); returns the binary's path."""
+    import subprocess
+    from flashpca_b200 import build
+    host = os.path.join(ROOT, "flashpca_b200", "host")
+    exe = os.path.join(str(out_dir), "eigen_adaptor_check")
+    subprocess.check_call(
+        ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+         "-I", host, "-I", os.path.join(ROOT, "tests", "eigen_stub"), "-o", exe,
+         os.path.join(ROOT, "tests", "eigen_adaptor_check.cpp"), os.path.join(host, "data.cpp"),
+         os.path.join(host, "util.cpp"), "-L", os.path.dirname(build.LIB), "-lflashpca_b200",
+         "-Wl,-rpath," + os.path.dirname(build.LIB)])
+    return exe
+
+
+def test_eigen_typed_operator_surface_compiles(native_lib, tmp_path):
+    """with <Eigen/Core> included first, SVDWideOnline exposes upstream's
+    exact block-variant signatures (svdwide.h:84-106, Eigen::MatrixXd in and out) and SVDWide
+    upstream's constructor (svdwide.h:18)."""
+    assert os.path.exists(build_eigen_adaptor_check(tmp_path))
+
+
 def test_no_cuda_means_loud_failure(native_lib):
     """Without a GPU the product path must fail, never fall back to a CPU path."""
     import torch
