@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-block", action="store_true", help="skip the k = 2 / k = 20 block ops")
     ap.add_argument("--no-cfg5", action="store_true", help="skip 1M x 500k at --gpus 8")
     ap.add_argument("--cfg5", action="store_true", help="force the 1M x 500k side measurement")
+    ap.add_argument("--cfg5-shape", default="1000000x500000",
+                    help="N x P of the side measurement (tests of the code path at small sizes)")
     ap.add_argument("--cpu-sample-snps", type=int, default=0)
     return ap.parse_args()
 
@@ -358,7 +360,7 @@ def run_b200(a):
     # ---- BASELINE configs[4]: 1,000,000 x 500,000, k=20, SNP-sharded over the 8 GPUs of the box
     cfg5 = None
     if (world >= 8 and (n, p) == (500000, 100000) and not a.no_cfg5) or a.cfg5:
-        n5, p5 = 1000000, 500000
+        n5, p5 = (int(v) for v in a.cfg5_shape.split("x"))
         spec5 = SynthSpec(n5, p5)
         a5, b5 = fdist.shard_range(p5, world, rank)
         t5 = time.perf_counter()

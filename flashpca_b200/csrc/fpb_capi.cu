@@ -213,6 +213,7 @@ struct fpb_handle {
   struct OpGraph {
     cudaGraphExec_t exec = nullptr;
     uint64_t launches = 0;
+    uint32_t seen = 0;
   };
   std::unordered_map<uint64_t, OpGraph> op_graphs;
   bool graphs_ok = true;           // cleared when a capture fails: plain launches from then on
@@ -1495,13 +1496,15 @@ int fpb_perform_op_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, doubl
 namespace {
 bool graph_capable(const fpb_handle* h) {
   static const bool off = getenv("FPB_GRAPH") && atoi(getenv("FPB_GRAPH")) == 0;
-  return !off && h->graphs_ok && h->kids.empty() && !h->dense && h->use_imma && !h->use_fused &&
-         !h->time_gemv;
+  // (not with a communicator attached: a captured ncclAllReduce next to the eager collectives of
+  // the host program's own communicator hung the 2-GPU run; the sharded path launches plainly)
+  return !off && h->graphs_ok && !h->comm && h->kids.empty() && !h->dense && h->use_imma &&
+         !h->use_fused && !h->time_gemv;
 }
 }  // namespace
 
-// y = X X' x, device pointers.  After one plain call per (x, y) pair (which also makes every lazily
-// allocated buffer exist) the op is captured once and replayed as a CUDA graph.
+// y = X X' x, device pointers.  A (x, y) pointer pair that comes back a third time is captured once
+// and replayed as a CUDA graph from then on.
 int fpb_perform_op_dev(fpb_handle* h, const double* d_x, double* d_y) {
   if (!h || !d_x || !d_y) FPB_FAIL(h, "null argument");
   if (!graph_capable(h)) return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
@@ -1509,13 +1512,13 @@ int fpb_perform_op_dev(fpb_handle* h, const double* d_x, double* d_y) {
   const uint64_t key = (uint64_t)(uintptr_t)d_x * 0x9E3779B97F4A7C15ull ^ (uint64_t)(uintptr_t)d_y;
   auto it = h->op_graphs.find(key);
   if (it == h->op_graphs.end()) {
-    if (h->op_graphs.size() >= 256) {  // bounded cache
-      for (auto& kv : h->op_graphs) cudaGraphExecDestroy(kv.second.exec);
-      h->op_graphs.clear();
-    }
-    h->op_graphs[key] = fpb_handle::OpGraph();  // seen once: capture on the next call
+    // pointer pairs that recur (the Lanczos loop's fixed buffers, the host API's staging buffers,
+    // a benchmark loop) get a graph on their third call; one-off pairs never pay for a capture
+    if (h->op_graphs.size() >= 64) return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
+    h->op_graphs[key] = fpb_handle::OpGraph();
     return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
   }
+  if (!it->second.exec && ++it->second.seen < 2) return fpb_perform_op_multi_dev(h, d_x, 1, d_y);
   if (!it->second.exec) {
     const uint64_t l0 = h->launches;
     cudaGraph_t graph = nullptr;

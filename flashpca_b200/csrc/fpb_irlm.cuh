@@ -153,6 +153,17 @@ __global__ void k_resid(const double* __restrict__ w, const double* __restrict__
   f[r] = v;
 }
 
+// out = out2 = a * x: the new Lanczos vector goes to its column of V and to the fixed buffer the
+// operator reads (one (x, y) pointer pair for every op of the solve: one CUDA graph, fpb_capi.cu)
+__global__ void k_scale2(double a, const double* __restrict__ x, double* __restrict__ out,
+                         double* __restrict__ out2, uint64_t n) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double v = a * x[r];
+  out[r] = v;
+  out2[r] = v;
+}
+
 // out = a * x + b * y  (y may be null)
 __global__ void k_axpby(double a, const double* x, double b, const double* y, double* out,
                         uint64_t n) {
@@ -453,7 +464,7 @@ class Irlm {
   cudaStream_t stream_;
   std::function<void(const double*, double*)> op_;
   double *dV_ = nullptr, *dF_ = nullptr, *dW_ = nullptr, *dVs_ = nullptr, *dPartial_ = nullptr,
-         *dSmall_ = nullptr, *dQ_ = nullptr;
+         *dSmall_ = nullptr, *dQ_ = nullptr, *dX_ = nullptr;
   uint32_t nblocks_ = 0, nblocks256_ = 0;
   double *dPartial2_ = nullptr, *dH_ = nullptr, *hPinned_ = nullptr;
   bool fused_ = false;
@@ -477,6 +488,7 @@ inline void Irlm::alloc() {
   cudaMalloc(&dVs_, sizeof(double) * n_ * ncv_);
   cudaMalloc(&dF_, sizeof(double) * n_);
   cudaMalloc(&dW_, sizeof(double) * n_);
+  cudaMalloc(&dX_, sizeof(double) * n_);
   cudaMalloc(&dPartial_, sizeof(double) * (size_t)nblocks_ * ncv_);
   cudaMalloc(&dSmall_, sizeof(double) * (ncv_ + 1));
   cudaMalloc(&dQ_, sizeof(double) * ncv_ * ncv_);
@@ -490,11 +502,11 @@ inline void Irlm::alloc() {
 }
 
 inline void Irlm::release() {
-  cudaFree(dV_); cudaFree(dVs_); cudaFree(dF_); cudaFree(dW_);
+  cudaFree(dV_); cudaFree(dVs_); cudaFree(dF_); cudaFree(dW_); cudaFree(dX_);
   cudaFree(dPartial_); cudaFree(dSmall_); cudaFree(dQ_);
   cudaFree(dPartial2_); cudaFree(dH_);
   if (hPinned_) cudaFreeHost(hPinned_);
-  dV_ = dVs_ = dF_ = dW_ = dPartial_ = dSmall_ = dQ_ = dPartial2_ = dH_ = hPinned_ = nullptr;
+  dV_ = dVs_ = dF_ = dW_ = dX_ = dPartial_ = dSmall_ = dQ_ = dPartial2_ = dH_ = hPinned_ = nullptr;
 }
 
 inline void Irlm::gemv_t(const double* V, uint32_t m, const double* f, double* host_out) {
@@ -545,9 +557,9 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
       restart = true;
     }
     double ta = now_s();
-    k_axpby<<<grid1d(256), 256, 0, stream_>>>(1.0 / beta, dF_, 0.0, nullptr, col(i), n_);
+    k_scale2<<<grid1d(256), 256, 0, stream_>>>(1.0 / beta, dF_, col(i), dX_, n_);
     H(i, i - 1) = restart ? 0.0 : beta;
-    op_(col(i), dW_);
+    op_(dX_, dW_);
     nops_++;
     double tb = now_s();
     double Hii;
@@ -635,8 +647,8 @@ inline void Irlm::run(uint32_t maxit, double tol, IrlmResult& res) {
   simple_random_vec(r0, n_, 0);
   cudaMemcpyAsync(dF_, r0.data(), sizeof(double) * n_, cudaMemcpyHostToDevice, stream_);
   double vnorm = norm(dF_);
-  k_axpby<<<grid1d(256), 256, 0, stream_>>>(1.0 / vnorm, dF_, 0.0, nullptr, col(0), n_);
-  op_(col(0), dW_);
+  k_scale2<<<grid1d(256), 256, 0, stream_>>>(1.0 / vnorm, dF_, col(0), dX_, n_);
+  op_(dX_, dW_);
   nops_++;
   double h00;
   gemv_t(col(0), 1, dW_, &h00);

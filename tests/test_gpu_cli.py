@@ -159,7 +159,7 @@ def test_nccl_sharded_two_gpus():
     script = os.path.join(ROOT, "tests", "_nccl_shard_worker.py")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                           "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
-                          "29617", script], capture_output=True, text=True, timeout=600)
+                          "29617", script], capture_output=True, text=True, timeout=180)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "NCCL_SHARD_OK" in out.stdout
 
