@@ -304,8 +304,13 @@ def run_b200(a):
     # stalled that rank's launches and doubled the N=2 mean)
     sampler = ClockSampler(local)
     sampler.start()
+    # NCCL announces its version on stdout when the first communicator comes up; stdout carries
+    # exactly one JSON line, so fd 1 points at stderr until the communicators exist
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
     lib = _lib.load()
 
     n, p, k = a.n, a.p, a.k
@@ -316,6 +321,14 @@ def run_b200(a):
     t_stage = time.perf_counter() - t_stage
     if world > 1:
         fdist.attach_nccl(op, world, rank)
+        y0 = torch.zeros(n, dtype=torch.float64, device="cuda")
+        y1 = torch.empty_like(y0)
+        _lib.check(lib.fpb_perform_op_dev(op.h, y0.data_ptr(), y1.data_ptr()), op.h)
+        _lib.check(lib.fpb_sync(op.h), op.h)      # first collective of the library's communicator
+        del y0, y1
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     sampler.wait_first()
 
     # ---- device-resident metric: exactly --steps ops, a CUDA event after each
