@@ -41,7 +41,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     sources.append(os.path.join(ROOT, "include", "flashpca_b200.h"))
     if not force and _newer(LIB, sources):
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, os.path.join(csrc, "fpb_capi.cu"), "-ldl"]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, os.path.join(csrc, "fpb_capi.cu"), "-ldl", "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

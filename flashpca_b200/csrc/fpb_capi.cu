@@ -28,6 +28,7 @@
 #include <chrono>
 #include <cmath>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1040,8 +1041,9 @@ int allreduce(fpb_handle* h, double* d_buf, size_t count) {
 }
 
 // Device -> pageable host copy through two pinned 16 MiB bounce buffers: the DMA of chunk c+1
-// overlaps the host memcpy of chunk c (a plain cudaMemcpy to pageable memory runs at ~4 GB/s,
-// 20 ms for the 80 MB of eigenvectors at N = 500k, k = 20).
+// overlaps the host copy of chunk c, and the host copy itself runs on four threads (the destination
+// is usually freshly allocated: the first touch of its pages, not the copy, is what costs -- a plain
+// cudaMemcpy to pageable memory runs at ~4 GB/s, 20 ms for the 80 MB of eigenvectors at N = 500k).
 int download_pageable(fpb_handle* h, void* dst, const void* d_src, size_t bytes) {
   constexpr size_t kChunk = 16u << 20;
   if (bytes <= (1u << 20)) {
@@ -1061,12 +1063,25 @@ int download_pageable(fpb_handle* h, void* dst, const void* d_src, size_t bytes)
                     h->stream);
     cudaEventRecord(h->ev_bounce[c & 1], h->stream);
   };
+  auto host_copy = [](char* to, const unsigned char* from, size_t len) {
+    constexpr int kThreads = 4;
+    const size_t per = ((len + kThreads - 1) / kThreads + 4095) & ~(size_t)4095;
+    std::thread th[kThreads - 1];
+    int started = 0;
+    for (int t = 1; t < kThreads; t++) {
+      const size_t o = (size_t)t * per;
+      if (o >= len) break;
+      th[started++] = std::thread([=] { memcpy(to + o, from + o, std::min(per, len - o)); });
+    }
+    memcpy(to, from, std::min(per, len));
+    for (int t = 0; t < started; t++) th[t].join();
+  };
   issue(0);
   for (size_t c = 0; c < nchunks; c++) {
     FPB_CUDA(h, cudaEventSynchronize(h->ev_bounce[c & 1]));
     if (c + 1 < nchunks) issue(c + 1);
     const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
-    memcpy((char*)dst + off, h->h_bounce[c & 1], len);
+    host_copy((char*)dst + off, h->h_bounce[c & 1], len);
   }
   FPB_CUDA(h, cudaGetLastError());
   return 0;

@@ -27,7 +27,8 @@ int ensure_umma(fpb_handle* h) {
   // second half: CTA = one 128-byte stripe x a split of the 128-row boxes; at most 1024 boxes
   // (131072 SNPs) per split: 131072 x 255 x 64 < 2^31
   U.nbox = (uint32_t)((h->nsnps + 127) / 128);
-  uint32_t sv = std::max<uint32_t>((U.nbox + 1023) / 1024, (4 * sm + U.nst - 1) / U.nst);
+  // (measured at 500k x 100k: 6 row splits 3.06 ms, 3 splits 3.27 ms per 8-column pass: ~32 waves)
+  uint32_t sv = std::max<uint32_t>((U.nbox + 1023) / 1024, (32 * sm + U.nst - 1) / U.nst);
   sv = std::max<uint32_t>(std::min<uint32_t>(sv, std::max<uint32_t>((U.nbox + 1023) / 1024, U.nbox / 8)), 1);
   U.bps_v = (U.nbox + sv - 1) / sv;
   U.splits_v = (U.nbox + U.bps_v - 1) / U.bps_v;
@@ -54,9 +55,9 @@ int ensure_umma(fpb_handle* h) {
                                    fpb::kUSmemBytes));
   FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_umma_xt<8, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpb::kUSmemBytes));
-  FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_umma_xv<4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_umma_xv<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpb::kUSmemBytes));
-  FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_umma_xv<8, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_umma_xv<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    fpb::kUSmemBytes));
   U.ready = true;
   return 0;
@@ -157,10 +158,10 @@ void umma_prod_block(fpb_handle* h, uint32_t nv, double* d_y) {
   }
   dim3 grid(U.nst, U.splits_v);
   if (NV == 4)
-    fpb::k_umma_xv<4, 2, 4><<<grid, (8 * 2 + 4 + 1) * 32, fpb::kUSmemBytes, h->stream>>>(
+    fpb::k_umma_xv<4, 4><<<grid, (8 + 4 + 1) * 32, fpb::kUSmemBytes, h->stream>>>(
         h->tm_f, (uint32_t)h->n, U.s_j, U.nbox, U.bps_v, U.part, U.vstride, U.sstride_v, U.err);
   else
-    fpb::k_umma_xv<8, 2, 4><<<grid, (8 * 2 + 4 + 1) * 32, fpb::kUSmemBytes, h->stream>>>(
+    fpb::k_umma_xv<8, 4><<<grid, (8 + 4 + 1) * 32, fpb::kUSmemBytes, h->stream>>>(
         h->tm_f, (uint32_t)h->n, U.s_j, U.nbox, U.bps_v, U.part, U.vstride, U.sstride_v, U.err);
   h->launches++;
   U.used = true;

@@ -408,45 +408,45 @@ k_umma_xt(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint8_t* __res
 // ---------------------------------------------------------------------------
 // Second half: F[i][v] = sum_j e_ij a_j^(v) from the same SNP-major copy.
 // CTA = one 128-byte column stripe (512 individuals) x one split of the 128-row SNP boxes.
-// A box is decoded by a pair of warpgroups (8 warps, warp = one 16-byte chunk of the stripe):
-// LDSM.MT1616 transposes bytes, so lane = packed byte column and K = SNPs.  The four cumulative
-// mask planes of a byte column are separate MMA rows (plane pair pp = p >> 1 selects the
-// accumulator, p & 1 the upper or lower 16 lanes of the warp's TMEM quadrant), and the epilogue
-// differences them into the four individuals of the byte.
+// A box is decoded by 8 warps (warp = one 16-byte chunk of the stripe): LDSM.MT1616 transposes
+// bytes, so lane = packed byte column and K = SNPs.  The four cumulative mask planes of a byte
+// column are separate MMA rows (plane pair pp = p >> 1 selects the accumulator, p & 1 the upper
+// or lower 16 lanes of the warp's TMEM quadrant), and the epilogue differences them into the four
+// individuals of the byte.
 // TMEM: D[hp] (hp = 2 h + pp, h = half of the stripe: 64 byte columns) at columns hp N: four
-// independent accumulator chains, issued K-block-major.  Staging: per warpgroup pair a private
-// ring of half-box slots (64 columns: hp 16 + kcl 8 for the K = 32 blocks 2 hb + kcl of the box).
-// NISS issuer warps share the accumulators by hp.
+// independent accumulators, one issuer warp each (NISS = 4) -- a box is one handshake and 4 MMAs
+// per issuer.  Staging: a ring of whole-box slots (128 columns: (hp 4 + kc) 8 for the K = 32 block
+// kc of the box) with one sequential producer (the 8 decoder warps move box by box together).
 // out[v * vstride + split * sstride + individual].
 // ---------------------------------------------------------------------------
-template <int NV, int NPAIR>
+template <int NV>
 struct UmmaXvCfg {
   static constexpr int N = 8 * NV;
   static constexpr int DCols = 4 * N;
-  static constexpr int NTPmax = ((512 - DCols) / 64) / NPAIR;  // half-box slots per pair
-  static constexpr int NTP = NTPmax > 4 ? 4 : NTPmax;
+  static constexpr int NTmax = (512 - DCols) / 128;  // whole-box staging slots
+  static constexpr int NT = NTmax > 3 ? 3 : NTmax;
   static constexpr int BBytes = 1024 * NV;  // digit slices of one 128-row box (4 K-blocks)
   static constexpr int NB = 4;
-  static constexpr int NAPmax = ((kUSmemBytes - 2048 - NB * BBytes) / kUBoxBytes) / NPAIR;
-  static constexpr int NAP = NAPmax > 4 ? 4 : NAPmax;  // boxes in flight per pair
-  static_assert(NTP >= 2, "TMEM: not enough columns for two staging slots per pair");
+  static constexpr int NAmax = (kUSmemBytes - 2048 - NB * BBytes) / kUBoxBytes;
+  static constexpr int NA = NAmax > 8 ? 8 : NAmax;  // boxes in flight
+  static_assert(NT >= 2, "TMEM: not enough columns for two staging slots");
 };
 
-template <int NV, int NPAIR, int NISS>
-__global__ void __launch_bounds__((8 * NPAIR + NISS + 1) * 32, 1)
+template <int NV, int NISS>
+__global__ void __launch_bounds__((8 + NISS + 1) * 32, 1)
 k_umma_xv(const __grid_constant__ TmaDesc tmap, uint32_t Cn /* output length */,
           const uint8_t* __restrict__ S, uint32_t nboxes_total, uint32_t boxes_per_split,
           double* __restrict__ out, uint64_t vstride, uint64_t sstride, uint32_t* __restrict__ gerr) {
-  using C = UmmaXvCfg<NV, NPAIR>;
-  constexpr int N = C::N, NTP = C::NTP, NAP = C::NAP, NB = C::NB;
-  constexpr int NW = 8 * NPAIR;  // decoder warps
+  using C = UmmaXvCfg<NV>;
+  constexpr int N = C::N, NT = C::NT, NA = C::NA, NB = C::NB;
+  constexpr int NW = 8;  // decoder warps
   static_assert(4 % NISS == 0, "issuers split the four accumulators");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_ring = base, b_ring = base + NPAIR * NAP * kUBoxBytes;
+  const uint32_t a_ring = base, b_ring = base + NA * kUBoxBytes;
   const uint32_t bars = b_ring + NB * C::BBytes;
-  constexpr int A_FULL = 0, A_EMPTY = NPAIR * NAP, B_FULL = 2 * NPAIR * NAP, B_EMPTY = B_FULL + NB,
-                T_FULL = B_EMPTY + NB, T_EMPTY = T_FULL + NPAIR * NTP, D_FULL = T_EMPTY + NPAIR * NTP,
+  constexpr int A_FULL = 0, A_EMPTY = NA, B_FULL = 2 * NA, B_EMPTY = B_FULL + NB,
+                T_FULL = B_EMPTY + NB, T_EMPTY = T_FULL + NT, D_FULL = T_EMPTY + NT,
                 NBARS = D_FULL + 1;
   const uint32_t misc = bars + 8 * NBARS;
   volatile uint32_t* misc_p =
@@ -459,16 +459,16 @@ k_umma_xv(const __grid_constant__ TmaDesc tmap, uint32_t Cn /* output length */,
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
 
   if (tid == 0) {
-    for (int i = 0; i < NPAIR * NAP; i++) {
+    for (int i = 0; i < NA; i++) {
       mbar_init(bar(A_FULL + i), 1);
-      mbar_init(bar(A_EMPTY + i), 8);
+      mbar_init(bar(A_EMPTY + i), NW);
     }
     for (int i = 0; i < NB; i++) {
       mbar_init(bar(B_FULL + i), 1);
       mbar_init(bar(B_EMPTY + i), NISS);
     }
-    for (int i = 0; i < NPAIR * NTP; i++) {
-      mbar_init(bar(T_FULL + i), 8);
+    for (int i = 0; i < NT; i++) {
+      mbar_init(bar(T_FULL + i), NW);
       mbar_init(bar(T_EMPTY + i), NISS);
     }
     mbar_init(bar(D_FULL), NISS);
@@ -485,7 +485,7 @@ k_umma_xv(const __grid_constant__ TmaDesc tmap, uint32_t Cn /* output length */,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc_p[0];
-  const uint32_t tA = tmem + (uint32_t)C::DCols;  // staging: pair pr, slot t at (pr NTP + t) 64
+  const uint32_t tA = tmem + (uint32_t)C::DCols;  // staging slot t at t 128
   const Watch watch{misc_p + 1, gerr};
 
   if (warp == NW + NISS) {
@@ -494,13 +494,13 @@ k_umma_xv(const __grid_constant__ TmaDesc tmap, uint32_t Cn /* output length */,
       const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
       bool ok = true;
       for (uint32_t i = 0; i < nbx && ok; i++) {
-        const uint32_t bs = i % NB, pr = i % NPAIR, m = i / NPAIR, as = pr * NAP + (m % NAP);
+        const uint32_t bs = i % NB, as = i % NA;
         if (i >= NB) ok = wait_bar(bar(B_EMPTY + bs), ((i / NB) - 1) & 1, watch, kUErrTimeout | 0x11);
         if (!ok) break;
         mbar_expect_tx(bar(B_FULL + bs), C::BBytes);
         bulk_load(b_ring + bs * C::BBytes, S + (uint64_t)(t_begin + i) * C::BBytes, C::BBytes,
                   bar(B_FULL + bs), pol_keep);
-        if (m >= NAP) ok = wait_bar(bar(A_EMPTY + as), ((m / NAP) - 1) & 1, watch, kUErrTimeout | 0x12);
+        if (i >= NA) ok = wait_bar(bar(A_EMPTY + as), ((i / NA) - 1) & 1, watch, kUErrTimeout | 0x12);
         if (!ok) break;
         mbar_expect_tx(bar(A_FULL + as), kUBoxBytes);
         tma_load_2d(a_ring + as * kUBoxBytes, &tmap, (int)xbyte0, (int)((t_begin + i) * kUBoxRows),
@@ -514,40 +514,34 @@ k_umma_xv(const __grid_constant__ TmaDesc tmap, uint32_t Cn /* output length */,
       const uint32_t idesc = umma_idesc(N);
       bool ok = true;
       for (uint32_t i = 0; i < nbx && ok; i++) {
-        const uint32_t bs = i % NB, pr = i % NPAIR, m = i / NPAIR;
+        const uint32_t bs = i % NB, ts = i % NT;
         ok = wait_bar(bar(B_FULL + bs), (i / NB) & 1, watch, kUErrTimeout | 0x13);
+        if (ok) ok = wait_bar(bar(T_FULL + ts), (i / NT) & 1, watch, kUErrTimeout | 0x14);
+        if (!ok) break;
+        tc_fence_after();
         const uint64_t bd0 = umma_bdesc(b_ring + bs * C::BBytes);
-#pragma unroll 1
-        for (uint32_t hb = 0; hb < 2 && ok; hb++) {
-          const uint32_t mm = m * 2 + hb, ts = mm % NTP;
-          ok = wait_bar(bar(T_FULL + pr * NTP + ts), (mm / NTP) & 1, watch, kUErrTimeout | 0x14);
-          if (!ok) break;
-          tc_fence_after();
-          const uint32_t slot = tA + (pr * NTP + ts) * 64;
+        const uint32_t slot = tA + ts * 128;
 #pragma unroll
-          for (uint32_t kcl = 0; kcl < 2; kcl++)
+        for (uint32_t hh = 0; hh < HPI; hh++)
 #pragma unroll
-            for (uint32_t hh = 0; hh < HPI; hh++) {
-              const uint32_t hp = iss * HPI + hh, kc = hb * 2 + kcl;
-              umma_i8(tmem + hp * N, slot + hp * 16 + kcl * 8, bd0 + (uint64_t)((kc * NV * 256) >> 4),
-                      idesc, (i > 0 || kc > 0) ? 1u : 0u);
-            }
-          umma_commit(bar(T_EMPTY + pr * NTP + ts));
-        }
-        if (ok) umma_commit(bar(B_EMPTY + bs));
+          for (uint32_t kc = 0; kc < 4; kc++) {
+            const uint32_t hp = iss * HPI + hh;
+            umma_i8(tmem + hp * N, slot + (hp * 4 + kc) * 8, bd0 + (uint64_t)((kc * NV * 256) >> 4),
+                    idesc, (i > 0 || kc > 0) ? 1u : 0u);
+          }
+        umma_commit(bar(T_EMPTY + ts));
+        umma_commit(bar(B_EMPTY + bs));
       }
       if (ok) umma_commit(bar(D_FULL));
     }
   } else {
-    const int wg = warp >> 2, q = warp & 3;
-    const uint32_t pr = (uint32_t)(wg >> 1), h = (uint32_t)(wg & 1);
-    const uint32_t ch = 4 * h + (uint32_t)q;  // 16-byte chunk of the stripe
-    const uint32_t lane_base = ((uint32_t)q * 32u) << 16;
+    const uint32_t h = (uint32_t)(warp >> 2), q = (uint32_t)(warp & 3);
+    const uint32_t ch = 4 * h + q;  // 16-byte chunk of the stripe
+    const uint32_t lane_base = (q * 32u) << 16;
     bool ok = true;
-    uint32_t m = 0;
-    for (uint32_t i = pr; i < nbx && ok; i += NPAIR, m++) {
-      const uint32_t as = pr * NAP + (m % NAP);
-      ok = wait_bar(bar(A_FULL + as), (m / NAP) & 1, watch, kUErrTimeout | 0x15);
+    for (uint32_t i = 0; i < nbx && ok; i++) {
+      const uint32_t as = i % NA, ts = i % NT;
+      ok = wait_bar(bar(A_FULL + as), (i / NA) & 1, watch, kUErrTimeout | 0x15);
       if (!ok) break;
       const uint32_t tile = a_ring + as * kUBoxBytes;
       uint32_t a[4][4];
@@ -559,43 +553,36 @@ k_umma_xv(const __grid_constant__ TmaDesc tmap, uint32_t Cn /* output length */,
                      : "=r"(a[kc][0]), "=r"(a[kc][1]), "=r"(a[kc][2]), "=r"(a[kc][3])
                      : "r"(addr));
       }
+      if (i >= NT) ok = wait_bar(bar(T_EMPTY + ts), ((i / NT) - 1) & 1, watch, kUErrTimeout | 0x16);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t slot = tA + ts * 128 + lane_base;
 #pragma unroll
-      for (uint32_t hb = 0; hb < 2; hb++) {
-        const uint32_t mm = m * 2 + hb, ts = mm % NTP;
-        if (mm >= NTP && ok)
-          ok = wait_bar(bar(T_EMPTY + pr * NTP + ts), ((mm / NTP) - 1) & 1, watch, kUErrTimeout | 0x16);
-        tc_fence_after();
-        const uint32_t slot = tA + (pr * NTP + ts) * 64 + lane_base;
+      for (uint32_t p = 0; p < 4; p++) {
+        const uint32_t mk = p == 0 ? 0x03030303u : p == 1 ? 0x0F0F0F0Fu : p == 2 ? 0x3F3F3F3Fu : 0xFFFFFFFFu;
+        uint32_t d[16];
 #pragma unroll
-        for (uint32_t p = 0; p < 4; p++) {
-          const uint32_t mk = p == 0 ? 0x03030303u : p == 1 ? 0x0F0F0F0Fu : p == 2 ? 0x3F3F3F3Fu : 0xFFFFFFFFu;
-          uint32_t d[8];
-#pragma unroll
-          for (int kcl = 0; kcl < 2; kcl++) {  // (a0, a2 | a1, a3): lanes g | g + 8, columns 2 q', 2 q' + 1
-            const int kc = hb * 2 + kcl;
-            d[4 * kcl + 0] = a[kc][0] & mk;
-            d[4 * kcl + 1] = a[kc][2] & mk;
-            d[4 * kcl + 2] = a[kc][1] & mk;
-            d[4 * kcl + 3] = a[kc][3] & mk;
-          }
-          const uint32_t hp = 2 * h + (p >> 1);
-          tmem_st_16x256b_x2(slot + hp * 16 + (((p & 1u) * 16u) << 16), d);
+        for (int kc = 0; kc < 4; kc++) {  // (a0, a2 | a1, a3): lanes g | g + 8, columns 2 q', 2 q' + 1
+          d[4 * kc + 0] = a[kc][0] & mk;
+          d[4 * kc + 1] = a[kc][2] & mk;
+          d[4 * kc + 2] = a[kc][1] & mk;
+          d[4 * kc + 3] = a[kc][3] & mk;
         }
-        if (hb == 1) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(A_EMPTY + as));
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(T_FULL + pr * NTP + ts));
+        const uint32_t hp = 2 * h + (p >> 1);
+        tmem_st_16x256b_x4(slot + hp * 32 + (((p & 1u) * 16u) << 16), d);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(A_EMPTY + as));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(T_FULL + ts));
     }
-    // epilogue: the first warpgroup pair reads the accumulators back
+    // epilogue: read the accumulators back
     if (nbx > 0 && ok) ok = wait_bar(bar(D_FULL), 0, watch, kUErrTimeout | 0x17);
     tc_fence_after();
-    if (pr == 0) {
+    {
       const int hi = lane >> 4, bc = lane & 15;
       const uint64_t bytecol = (uint64_t)xbyte0 + ch * 16 + bc;
 #pragma unroll 1

@@ -190,18 +190,18 @@ static float run_xv(const Problem& P, const uint8_t* S, uint32_t splits, double*
                     uint64_t sstride, int reps) {
   const uint32_t nboxes = (P.rows + 127) / 128;
   const uint32_t bps = (nboxes + splits - 1) / splits;
-  auto kern = k_umma_xv<NV, NPAIR, NISS>;
+  auto kern = k_umma_xv<NV, NISS>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
   dim3 grid((uint32_t)((P.pitch + 127) / 128), splits);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  kern<<<grid, (8 * NPAIR + NISS + 1) * 32, kUSmemBytes>>>(P.tm, (uint32_t)P.n, S, nboxes, bps, part, vstride, sstride, d_err);
+  kern<<<grid, (8 + NISS + 1) * 32, kUSmemBytes>>>(P.tm, (uint32_t)P.n, S, nboxes, bps, part, vstride, sstride, d_err);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
   for (int r = 0; r < reps; r++)
-    kern<<<grid, (8 * NPAIR + NISS + 1) * 32, kUSmemBytes>>>(P.tm, (uint32_t)P.n, S, nboxes, bps, part, vstride, sstride, d_err);
+    kern<<<grid, (8 + NISS + 1) * 32, kUSmemBytes>>>(P.tm, (uint32_t)P.n, S, nboxes, bps, part, vstride, sstride, d_err);
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms = 0;
@@ -408,16 +408,12 @@ int main(int argc, char** argv) {
   k_fill<<<148 * 8, 256>>>(P.g, P.rows, P.pitch, P.n, 99);
   CK(cudaDeviceSynchronize());
   if (make_map(P.g, P.pitch, P.rows, &P.tm, 128)) return 1;
-  timing<1, 2, 1, 1, 1>(P, 8, 3, 5);
-  timing<1, 2, 4, 1, 2>(P, 8, 3, 5);
-  timing<1, 4, 1, 2, 1>(P, 8, 3, 5);
-  timing<1, 4, 4, 2, 4>(P, 8, 3, 5);
-  timing<2, 4, 2, 2, 2>(P, 8, 3, 5);
-  timing<4, 4, 1, 2, 2>(P, 8, 3, 5);
-  timing<4, 4, 2, 1, 4>(P, 8, 3, 5);
-  timing<8, 4, 1, 2, 1>(P, 8, 3, 5);
+  timing<1, 4, 1, 1, 4>(P, 8, 3, 5);
+  timing<4, 4, 1, 1, 4>(P, 8, 3, 5);
+  timing<4, 4, 1, 1, 2>(P, 8, 3, 5);
+  timing<8, 4, 1, 1, 4>(P, 8, 3, 5);
   timing<8, 4, 1, 1, 2>(P, 8, 3, 5);
-  timing<8, 2, 1, 2, 4>(P, 8, 3, 5);
-  timing<8, 4, 1, 2, 4>(P, 16, 6, 5);
+  timing<8, 4, 1, 1, 1>(P, 8, 3, 5);
+  timing<8, 4, 1, 1, 4>(P, 8, 6, 5);
   return 0;
 }
