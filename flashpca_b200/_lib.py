@@ -49,6 +49,7 @@ SIGNATURES = {
     "fpb_comm_init": (_i, [_vp, _vp, _i, _i]),
     "fpb_pca": (_i, [_vp, _u32, _u32, _u32, _d, _vp, _vp, _c.POINTER(_u32), _c.POINTER(_u32),
                      _c.POINTER(_u32)]),
+    "fpb_pca_block": (_i, [_vp, _u32, _u32, _u32, _d, _vp, _vp, _c.POINTER(_u32), _c.POINTER(_u32)]),
     "fpb_pca_residual": (_i, [_vp, _d, _vp, _u32]),
     "fpb_pca_op_times": (_u32, [_vp, _vp, _u32]),
     "fpb_pca_phase_times": (None, [_vp, _vp]),

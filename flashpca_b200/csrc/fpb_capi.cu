@@ -40,6 +40,7 @@
 #include "fpb_fused.cuh"
 #include "fpb_imma.cuh"
 #include "fpb_irlm.cuh"
+#include "fpb_block.cuh"
 #include "fpb_kernels.cuh"
 #include "fpb_umma.cuh"
 
@@ -219,6 +220,8 @@ struct fpb_handle {
   std::unordered_map<uint64_t, OpGraph> op_graphs;
   bool graphs_ok = true;           // cleared when a capture fails: plain launches from then on
   fpb::Irlm* solver = nullptr;  // Lanczos workspace, kept between fpb_pca calls
+  fpb::BlockKrylov* bsolver = nullptr;  // block Krylov workspace (fpb_pca_block)
+  bool last_solve_block = false;        // which solver holds the eigenvectors of the last solve
   // fpb_time_perform_op: events bracketing the two contraction-kernel launches
   bool time_gemv = false;
   cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1325,6 +1328,7 @@ void fpb_destroy(fpb_handle* h) {
   cudaFree(h->d_ytmp);
   if (h->copy) cudaStreamDestroy(h->copy);
   delete h->solver;
+  delete h->bsolver;
   for (int i = 0; i < 4; i++)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -1701,6 +1705,7 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
   FPB_CUDA(h, cudaGetLastError());
   if (evals_out) memcpy(evals_out, res.evals.data(), sizeof(double) * nev);
   h->last_evals = res.evals;
+  h->last_solve_block = false;
   auto t2 = t1, t3 = t1;
   if (evecs_out) {
     if (ensure_staging(h, 0, (size_t)h->n * nev)) return 1;
@@ -1723,13 +1728,69 @@ int fpb_pca(fpb_handle* h, uint32_t nev, uint32_t ncv, uint32_t maxiter, double 
   return 0;
 }
 
+int fpb_pca_block(fpb_handle* h, uint32_t nev, uint32_t block, uint32_t max_passes, double tol,
+                  double* evals_out, double* evecs_out, uint32_t* nconv_out, uint32_t* npasses_out) {
+  if (!h) FPB_FAIL(h, "null argument");
+  if (block == 0) block = fpb::kBlkMaxB;
+  if (max_passes == 0) max_passes = 40;
+  if (nev < 1 || block > (uint32_t)fpb::kBlkMaxB || (uint64_t)nev + block > h->n)
+    FPB_FAIL(h, "invalid nev/block (need 1 <= nev, block <= 8, nev + block <= N)");
+  max_passes = (uint32_t)std::min<uint64_t>(max_passes, h->n / block);
+  if ((uint64_t)block * max_passes < nev) FPB_FAIL(h, "max_passes too small for nev");
+  FPB_CUDA(h, cudaSetDevice(h->device));
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  const auto t0 = now();
+  auto op = [h](const double* d_in, uint32_t k, double* d_out) -> int {
+    return fpb_perform_op_multi_dev(h, d_in, k, d_out);
+  };
+  if (h->bsolver && !h->bsolver->matches(h->n, nev, block, max_passes)) {
+    delete h->bsolver;
+    h->bsolver = nullptr;
+  }
+  if (!h->bsolver) h->bsolver = new fpb::BlockKrylov(h->n, nev, block, max_passes, h->stream, op);
+  else h->bsolver->set_op(op);
+  fpb::BlockResult res;
+  const int rc = h->bsolver->run(tol, res);
+  const auto t1 = now();
+  if (getenv("FPB_IRLM_TRACE"))
+    fprintf(stderr, "[block] %u passes: operator + V'AV %.1f ms, orthogonalisation %.1f ms, Rayleigh-Ritz %.1f ms\n",
+            res.npasses, h->bsolver->t_op * 1e3, h->bsolver->t_orth * 1e3, h->bsolver->t_ritz * 1e3);
+  if (rc || check_async(h)) {
+    if (rc) FPB_FAIL(h, h->bsolver->error.empty() ? std::string("block Krylov solve failed") : h->bsolver->error);
+    return 1;
+  }
+  FPB_CUDA(h, cudaGetLastError());
+  if (evals_out) memcpy(evals_out, res.evals.data(), sizeof(double) * nev);
+  h->last_evals = res.evals;
+  h->last_solve_block = true;
+  auto t2 = t1;
+  if (evecs_out) {
+    if (download_pageable(h, evecs_out, h->bsolver->eigenvectors(), sizeof(double) * h->n * nev)) return 1;
+    t2 = now();
+  }
+  h->pca_phase_s[0] = secs(t0, t1);
+  h->pca_phase_s[1] = 0.0;
+  h->pca_phase_s[2] = secs(t1, t2);
+  h->pca_phase_s[3] = secs(t0, t2);
+  if (nconv_out) *nconv_out = res.nconv;
+  if (npasses_out) *npasses_out = res.npasses;
+  return 0;
+}
+
 int fpb_pca_residual(fpb_handle* h, double div, double* err_out, uint32_t nev) {
   if (!h || !err_out || !(div > 0.0)) FPB_FAIL(h, "null argument");
-  if (!h->solver || h->last_evals.size() != nev || nev == 0)
+  if ((h->last_solve_block ? !h->bsolver : !h->solver) || h->last_evals.size() != nev || nev == 0)
     FPB_FAIL(h, "fpb_pca_residual: no fpb_pca result with this many eigenvectors on the handle");
   FPB_CUDA(h, cudaSetDevice(h->device));
   if (ensure_staging(h, (size_t)h->n * nev + nev, (size_t)h->n * nev + nev)) return 1;
-  h->solver->eigenvectors(h->d_in);  // U, N x nev
+  if (h->last_solve_block)
+    FPB_CUDA(h, cudaMemcpyAsync(h->d_in, h->bsolver->eigenvectors(), sizeof(double) * h->n * nev,
+                                cudaMemcpyDeviceToDevice, h->stream));
+  else
+    h->solver->eigenvectors(h->d_in);  // U, N x nev
   if (fpb_perform_op_multi_dev(h, h->d_in, nev, h->d_out)) return 1;  // all-reduced when sharded
   double* d_lam = h->d_in + (size_t)h->n * nev;
   double* d_err = h->d_out + (size_t)h->n * nev;

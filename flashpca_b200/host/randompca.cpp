@@ -1,5 +1,7 @@
 #include "randompca.hpp"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <cmath>
 #include <iostream>
@@ -23,12 +25,24 @@ static void finish_pca(RandomPCA& r, Op& op, unsigned int N, unsigned int p, uns
   r.U = Matrix(N, ndim);
   Vector evals(ndim);
   uint32_t nconv = 0, nops_ = 0, niter = 0;
-  if (fpb_pca(op.handle(), ndim, ndim * 2 + 1, maxiter, tol, evals.data(), r.U.data(), &nconv,
-              &nops_, &niter))
-    throw std::runtime_error(fpb_last_error(op.handle()));
+  // FPB_SOLVER=block selects the block Krylov solver (an extension: 8 columns per pass over the
+  // matrix on the tcgen05 kernels, Spectra's convergence criterion); default = Spectra's schedule
+  const char* sv = getenv("FPB_SOLVER");
+  if (sv && std::string(sv) == "block" && (uint64_t)ndim + 8 <= N) {
+    uint32_t npasses = 0;
+    if (fpb_pca_block(op.handle(), ndim, 8, 0, tol, evals.data(), r.U.data(), &nconv, &npasses))
+      throw std::runtime_error(fpb_last_error(op.handle()));
+    nops_ = 8 * npasses;
+    r.verbose&& std::cout << timestamp() << "Block Krylov solver: " << npasses
+                          << " passes of 8 columns" << std::endl;
+  } else {
+    if (fpb_pca(op.handle(), ndim, ndim * 2 + 1, maxiter, tol, evals.data(), r.U.data(), &nconv,
+                &nops_, &niter))
+      throw std::runtime_error(fpb_last_error(op.handle()));
+    r.verbose&& std::cout << timestamp() << "Matrix operations: " << nops_
+                          << ", restarts: " << (niter - 1) << std::endl;
+  }
   r.nops = nops_;
-  r.verbose&& std::cout << timestamp() << "Matrix operations: " << nops_
-                        << ", restarts: " << (niter - 1) << std::endl;
   if (nconv < ndim)
     // upstream throws a *pointer* here (randompca.cpp:160-165, 212-217) and main's catch(...)
     // reports an unknown exception; a value is thrown instead so the message survives.

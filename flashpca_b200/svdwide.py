@@ -202,6 +202,19 @@ class SVDWideOnline:
         return dict(values=evals, vectors=evecs, nconv=nconv.value, nops=nops.value,
                     niter=niter.value)
 
+    def pca_block(self, nev: int, tol: float, block: int = 8, max_passes: int = 40,
+                  want_vectors: bool = True):
+        """Block Krylov solve (extension, include/flashpca_b200.h fpb_pca_block): same result fields
+        as pca(); `npasses` = operator passes of `block` columns."""
+        evals = np.zeros(nev)
+        evecs = np.zeros((self.n, nev), order="F") if want_vectors else None
+        nconv, npasses = ctypes.c_uint32(), ctypes.c_uint32()
+        check(self.lib.fpb_pca_block(self.h, nev, block, max_passes, float(tol), evals.ctypes.data,
+                                     evecs.ctypes.data if want_vectors else None, ctypes.byref(nconv),
+                                     ctypes.byref(npasses)), self.h)
+        return dict(values=evals, vectors=evecs, nconv=nconv.value, npasses=npasses.value,
+                    nops=npasses.value * block)
+
     def pca_residual(self, nev: int, div: float) -> np.ndarray:
         """randompca.cpp:663-703 on the solver's own eigenpairs, computed on the device:
         err_j = ||X X' u_j / div - u_j d_j||^2 (collective when SNP-sharded)."""

@@ -126,6 +126,24 @@ def test_cli_default_precision_and_errors(cli, tmp_path):
     assert bad.returncode != 0 and "cannot specify both --memory and --blocksize" in bad.stderr
 
 
+def test_cli_block_solver_extension(cli, tmp_path):
+    """FPB_SOLVER=block: the command line with the block Krylov solver writes the same outputs."""
+    stem = FIXTURES["hapmap3"]
+    env = dict(os.environ, FPB_SOLVER="block")
+    out = subprocess.run([cli, "--bfile", stem, "--ndim", "10", "--notime", "--precision", "12", "-v",
+                          "--suffix", ".blk"], cwd=tmp_path, capture_output=True, text=True,
+                         timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Block Krylov solver:" in out.stdout
+    _, payload, n, p = load_fixture("hapmap3")
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, 10)
+    ev = np.loadtxt(tmp_path / "eigenvalues.blk")
+    assert np.abs(ev / ref["d"] - 1).max() < 1e-6
+    _, _, u = _read_table(tmp_path / "eigenvectors.blk")
+    assert np.abs(O.sign_align(u, ref["U"]) - ref["U"]).max() < 5e-6
+
+
 def test_cli_ndim_beyond_63(cli, tmp_path):
     """`--ndim 100` (ncv = 201) and the reference's own maximum on this fileset, 478
     (flashpca.cpp:623-633): accepted by the guard AND by the solver."""

@@ -328,6 +328,56 @@ def test_pca_large_ndim(native_lib, name, ndim):
     op.close()
 
 
+@pytest.mark.parametrize("name,ndim", [("data_chr1", 10), ("hapmap3", 10), ("hapmap3", 20)])
+def test_block_krylov_solver_vs_dense_eigh(native_lib, monkeypatch, name, ndim):
+    """fpb_pca_block (extension): block Lanczos on the tcgen05 block operator, Spectra's convergence
+    criterion.  Converged eigenpairs against dense eigh with the tolerances of the single-vector
+    solver (eigenvalues 1e-6 at tol 1e-6; vectors 1e-6 sign-aligned at a tighter tol), against the
+    Spectra-schedule solver, and through the reference's --check criterion."""
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    _, payload, n, p = load_fixture(name)
+    x, _ = O.dense_standardise(O.dense_codes(payload, n, p))
+    ref = O.dense_pca(x, ndim)
+    op = _mk(payload, n, p)
+    got = op.pca_block(ndim, 1e-6)
+    assert got["nconv"] == ndim and 3 <= got["npasses"] <= 40
+    assert np.abs(got["values"] / p / ref["d"] - 1).max() < 1e-6
+    err = op.pca_residual(ndim, float(p))
+    assert err.sum() / (n * ndim) < 1e-8
+    single = op.pca(ndim, 2 * ndim + 1, 500, 1e-6)
+    assert np.abs(got["values"] / single["values"] - 1).max() < 1e-6
+    tight = op.pca_block(ndim, 1e-10)
+    assert tight["nconv"] == ndim
+    u = O.sign_align(tight["vectors"], ref["U"])
+    assert np.abs(u - ref["U"]).max() < 1e-6
+    assert np.abs(tight["vectors"].T @ tight["vectors"] - np.eye(ndim)).max() < 1e-10
+    again = op.pca_block(ndim, 1e-6)
+    assert np.array_equal(again["values"], got["values"])      # bit-reproducible
+    op.close()
+
+
+def test_block_krylov_solver_synthetic_and_errors(native_lib, monkeypatch):
+    monkeypatch.delenv("FPB_PATH", raising=False)
+    from flashpca_b200._lib import FpbError
+    from flashpca_b200.synth import SynthSpec
+    s = SynthSpec(20011, 6000, seed=4, fst=0.05)
+    op = s.create_operator()
+    got = op.pca_block(20, 1e-6)
+    single = op.pca(20, 41, 500, 1e-6)
+    assert got["nconv"] == 20
+    assert np.abs(got["values"] / single["values"] - 1).max() < 1e-6
+    assert got["nops"] < 4 * single["nops"]
+    err = op.pca_residual(20, float(s.p))
+    assert err.sum() / (s.n * 20) < 1e-8
+    with pytest.raises(FpbError, match="invalid nev/block"):
+        op.pca_block(20, 1e-6, block=9)
+    with pytest.raises(FpbError, match="max_passes too small"):
+        op.pca_block(20, 1e-6, block=4, max_passes=2)
+    few = op.pca_block(20, 1e-12, max_passes=4)         # runs out of passes: reports what converged
+    assert few["nconv"] < 20 and few["npasses"] == 4
+    op.close()
+
+
 def test_solve_parity_at_10k_x_100k(native_lib, monkeypatch):
     """BASELINE configs[1] (synthetic 10,000 x 100,000, k = 20): the full GPU solve against the CPU
     oracle's solve (C restatement of the operator under the oracle's Spectra restatement) on the
