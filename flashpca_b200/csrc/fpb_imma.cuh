@@ -1446,7 +1446,8 @@ k_bcsr_count(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ c
     atomicAdd(counts + (uint64_t)(colidx[k] / kGatherTile) * nrows + r, 1u);
 }
 
-// sizes[t * nblk + b] = 32 * (longest row of block b in tile t); one warp per (t, b)
+// sizes[t * nblk + b] = 32 * (longest row of block b in tile t, rounded up to 8 entries -- a lane
+// reads its row 8 entries = one 16-byte load at a time); one warp per (t, b)
 __global__ void __launch_bounds__(256)
 k_sell_sizes(const uint32_t* __restrict__ counts, uint64_t nrows, uint32_t nblk, uint32_t ntiles,
              uint32_t* __restrict__ sizes) {
@@ -1458,7 +1459,7 @@ k_sell_sizes(const uint32_t* __restrict__ counts, uint64_t nrows, uint32_t nblk,
   uint32_t c = r < nrows ? counts[(uint64_t)t * nrows + r] : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
-  if (lane == 0) sizes[w] = c * 32u;
+  if (lane == 0) sizes[w] = ((c + 7u) & ~7u) * 32u;
 }
 
 // scatter the CSR entries into their SELL-32 slots (col16 pre-filled with the sentinel)
@@ -1475,8 +1476,9 @@ k_sell_fill(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ co
     uint64_t before = 0;  // entries of this row in earlier tiles (columns ascend within a row)
     for (uint32_t tt = 0; tt < t; tt++) before += counts[(uint64_t)tt * nrows + r];
     const uint64_t rank = k - b - before;
-    col16[blkoff[(uint64_t)t * nblk + (r >> 5)] + rank * 32 + (r & 31)] =
-        (uint16_t)(c - t * kGatherTile);
+    // group of 8 entries of lane (r & 31): [group][lane][8]
+    col16[blkoff[(uint64_t)t * nblk + (r >> 5)] + (rank >> 3) * 256 + (uint64_t)(r & 31) * 8 +
+          (rank & 7)] = (uint16_t)(c - t * kGatherTile);
   }
 }
 
@@ -1514,7 +1516,6 @@ k_sell_gather(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ 
   }
   for (; b < b1; b += NW) {
     const uint32_t width = (uint32_t)((onext - o) >> 5);
-    const uint16_t* cp = col16 + o + lane;
     // pointers of the warp's next block, fetched while this one is processed
     uint64_t o2 = 0, o2next = 0;
     if (b + NW < b1) {
@@ -1522,17 +1523,27 @@ k_sell_gather(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ 
       o2next = bo[b + NW + 1];
     }
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (uint32_t i = 0; i < width; i += 16) {
-      uint16_t c[16];
+    // width is a multiple of 8: groups of 8 entries per lane, one 16-byte load each (512 B per
+    // warp and load, four loads in flight -- the u16 loads of round 1 kept ~1 KB per warp in
+    // flight and left the kernel latency-bound at 2.4 TB/s)
+    const uint4* gp = reinterpret_cast<const uint4*>(col16 + o) + lane;
+    const uint32_t ngroups = width >> 3;
+    for (uint32_t gi = 0; gi < ngroups; gi += 4) {
+      uint4 v[4];
 #pragma unroll
-      for (int m = 0; m < 16; m++)  // 16 independent coalesced loads in flight
-        c[m] = (i + m < width) ? cp[(i + m) * 32] : (uint16_t)kGatherSentinel;
+      for (int m = 0; m < 4; m++)
+        v[m] = (gi + m < ngroups) ? gp[(uint64_t)(gi + m) * 32]
+                                  : make_uint4(0x30303030u, 0x30303030u, 0x30303030u, 0x30303030u);
 #pragma unroll
-      for (int m = 0; m < 16; m += 4) {
-        s0 += xs[c[m]];
-        s1 += xs[c[m + 1]];
-        s2 += xs[c[m + 2]];
-        s3 += xs[c[m + 3]];
+      for (int m = 0; m < 4; m++) {
+        s0 += xs[v[m].x & 0xFFFFu];
+        s1 += xs[v[m].x >> 16];
+        s2 += xs[v[m].y & 0xFFFFu];
+        s3 += xs[v[m].y >> 16];
+        s0 += xs[v[m].z & 0xFFFFu];
+        s1 += xs[v[m].z >> 16];
+        s2 += xs[v[m].w & 0xFFFFu];
+        s3 += xs[v[m].w >> 16];
       }
     }
     const uint64_t r = (uint64_t)b * 32 + lane;
