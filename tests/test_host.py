@@ -58,6 +58,23 @@ def test_eigen_typed_operator_surface_compiles(native_lib, tmp_path):
     assert os.path.exists(build_eigen_adaptor_check(tmp_path))
 
 
+def test_block_solver_host_eigensolver(tmp_path):
+    """fpb::sym_eigen (Householder + implicit QL, the m x m projected problem of fpb_pca_block) on
+    random symmetric matrices up to 208 x 208: residual and orthogonality at rounding level.  Host code
+    of a .cuh header: compiled with nvcc, run on the CPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "sym_eigen_check")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-I", os.path.join(ROOT, "flashpca_b200", "csrc"), "-o", exe,
+                           os.path.join(ROOT, "tests", "native", "sym_eigen_check.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
 def test_no_cuda_means_loud_failure(native_lib):
     """Without a GPU the product path must fail, never fall back to a CPU path."""
     import torch
