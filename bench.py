@@ -345,6 +345,7 @@ def run_b200(a):
         _lib.check(lib.fpb_perform_op_dev(op.h, y0.data_ptr(), y1.data_ptr()), op.h)
         _lib.check(lib.fpb_sync(op.h), op.h)      # first collective of the library's communicator
         del y0, y1
+    shard_sum = fdist.comm_kind(op)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
@@ -534,7 +535,10 @@ def run_b200(a):
         "data": "synthetic",
         "config": {"workload": workload_name(a), "n": n, "p": p, "k": k,
                    "path": "fused single-pass" if fused else "two-kernel",
-                   "sharding": "snp-columns x%d, 1 ncclAllReduce(f64, N) per step" % world
+                   "sharding": ("snp-columns x%d, shard sum of the N-vector per step: %s" % (world, {
+                       "peer": "one kernel over NVLink peer memory, fused with the op's finalize "
+                               "step (csrc/fpb_peer.cuh)",
+                       "nccl": "ncclAllReduce(f64, N)"}[shard_sum]))
                    if world > 1 else "single GPU",
                    "l2": "inputs %.1f GB per GPU >> 126 MB L2; no flush between steps"
                          % (npb * (j1 - j0) / 1e9),

@@ -47,6 +47,8 @@ SIGNATURES = {
     "fpb_sync": (_i, [_vp]),
     "fpb_comm_unique_id": (_i, [_vp]),
     "fpb_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "fpb_comm_kind": (_i, [_vp]),
+    "fpb_comm_link_local": (_i, [_vp, _i]),
     "fpb_pca": (_i, [_vp, _u32, _u32, _u32, _d, _vp, _vp, _c.POINTER(_u32), _c.POINTER(_u32),
                      _c.POINTER(_u32)]),
     "fpb_pca_block": (_i, [_vp, _u32, _u32, _u32, _d, _vp, _vp, _c.POINTER(_u32), _c.POINTER(_u32)]),

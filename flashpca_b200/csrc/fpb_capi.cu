@@ -43,6 +43,7 @@
 #include "fpb_block.cuh"
 #include "fpb_kernels.cuh"
 #include "fpb_umma.cuh"
+#include "fpb_peer.cuh"
 
 namespace {
 
@@ -65,6 +66,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;  // optional
   int (*CommDestroy)(NcclComm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load(std::string& err) {
@@ -82,6 +84,8 @@ struct NcclApi {
     CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(
         lib, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(
+        lib, "ncclAllGather");
     CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
@@ -207,6 +211,18 @@ struct fpb_handle {
   double trace = 0.0;
   NcclComm comm = nullptr;
   int nranks = 1, rank = 0;
+  // peer-memory shard sum (fpb_peer.cuh, fpb_host_peer.inl): replaces ncclAllReduce when the
+  // exchange regions of all ranks could be mapped
+  struct Peer {
+    bool ok = false;
+    void* region = nullptr;                     // this rank's exchange region
+    void* mapped[fpb::kPeerMax] = {};           // IPC mappings of the other ranks' regions
+    fpb::PeerView view = {};
+    uint64_t cap = 0;                           // doubles per exchange
+    bool fuse = false;                          // the op in flight may sum inside its finalize kernel
+    bool summed = false;                        // ... and did
+    bool used = false;
+  } P;
   uint64_t launches = 0;
   std::vector<float> op_ms;
   std::vector<double> last_evals;  // Ritz values of the last fpb_pca call (fpb_pca_residual)
@@ -945,6 +961,8 @@ void imma_crossprod(fpb_handle* h, const double* d_x, double* d_t, bool second_h
   h->launches++;
 }
 
+void peer_finalize_prod(fpb_handle* h, uint32_t nsplits, double* d_y);
+
 // second half from a, corr and the (max|a|, sum b) partials already in the handle
 void imma_prod_tail(fpb_handle* h, double* d_y) {
   static const bool gather_after = getenv("FPB_DEBUG_GATHER_AFTER") != nullptr;
@@ -955,6 +973,7 @@ void imma_prod_tail(fpb_handle* h, double* d_y) {
   const uint32_t nsplits = imma_contract(h, false, h->d_a, h->nsnps, 1);
   if (h->nmissing && gather_after) gather_launch(h, false, h->d_corr);
   if (h->nmissing) join_gather(h);
+  if (h->P.ok && h->P.fuse) return peer_finalize_prod(h, nsplits, d_y);
   uint32_t gb = (uint32_t)((h->n + 255) / 256);
   fpb::k_finalize_prod<<<gb, 256, 0, h->stream>>>(h->d_part, nsplits, h->part_stride, h->n,
                                                   h->d_sc + 1, h->nmissing ? h->d_mc : nullptr,
@@ -968,9 +987,12 @@ void imma_prod_tail(fpb_handle* h, double* d_y) {
 
 #include "fpb_host_umma.inl"
 
+#include "fpb_host_peer.inl"
+
 // device-reported protocol failures of the persistent / tcgen05 kernels, at the API's sync points
 int check_async(fpb_handle* h) {
   if (check_fused(h)) return 1;
+  if (check_peer(h)) return 1;
   return check_umma(h);
 }
 
@@ -1034,7 +1056,10 @@ void launch_perform_op(fpb_handle* h, const double* d_x, double* d_y) {
   }
 }
 
+int peer_allreduce(fpb_handle* h, double* d_buf, size_t count);
+
 int allreduce(fpb_handle* h, double* d_buf, size_t count) {
+  if (h->P.ok) return peer_allreduce(h, d_buf, count);
   if (!h->comm) return 0;
   int rc = g_nccl.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
   if (rc != 0)
@@ -1331,6 +1356,7 @@ void fpb_destroy(fpb_handle* h) {
   delete h->bsolver;
   for (int i = 0; i < 4; i++)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
+  peer_release(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_X);
   cudaFree(h->d_gs);
@@ -1483,8 +1509,13 @@ int fpb_prod_multi_dev(fpb_handle* h, const double* d_v, uint32_t k, double* d_y
       imma_prod_tail_pair(h, d_y + (uint64_t)c * h->n, d_y + (uint64_t)(c + 1) * h->n);
     }
   }
+  // a single column may sum the shards inside its finalize kernel (fpb_peer.cuh)
+  h->P.fuse = h->P.ok && k == 1;
+  h->P.summed = false;
   for (; c < k; c++) launch_prod(h, d_v + (uint64_t)c * h->nsnps, d_y + (uint64_t)c * h->n);
+  h->P.fuse = false;
   if (check_launch(h)) return 1;
+  if (h->P.summed) return 0;
   return allreduce(h, d_y, (size_t)h->n * k);
 }
 
@@ -1507,17 +1538,22 @@ int fpb_perform_op_multi_dev(fpb_handle* h, const double* d_m, uint32_t k, doubl
       imma_prod_tail_pair(h, d_y + (uint64_t)c * h->n, d_y + (uint64_t)(c + 1) * h->n);
     }
   }
+  h->P.fuse = h->P.ok && k == 1;
+  h->P.summed = false;
   for (; c < k; c++) launch_perform_op(h, d_m + (uint64_t)c * h->n, d_y + (uint64_t)c * h->n);
+  h->P.fuse = false;
   if (check_launch(h)) return 1;
+  if (h->P.summed) return 0;
   return allreduce(h, d_y, (size_t)h->n * k);
 }
 
 namespace {
 bool graph_capable(const fpb_handle* h) {
   static const bool off = getenv("FPB_GRAPH") && atoi(getenv("FPB_GRAPH")) == 0;
-  // (not with a communicator attached: a captured ncclAllReduce next to the eager collectives of
-  // the host program's own communicator hung the 2-GPU run; the sharded path launches plainly)
-  return !off && h->graphs_ok && !h->comm && h->kids.empty() && !h->dense && h->use_imma &&
+  // (not with NCCL's all-reduce inside: a captured ncclAllReduce next to the eager collectives of
+  // the host program's own communicator hung the 2-GPU run; the peer-memory shard sum is a plain
+  // kernel and replays with the rest of the op)
+  return !off && h->graphs_ok && (!h->comm || h->P.ok) && h->kids.empty() && !h->dense && h->use_imma &&
          !h->use_fused && !h->time_gemv;
 }
 }  // namespace
@@ -1630,6 +1666,8 @@ int fpb_get_dense(fpb_handle* h, double* out_x) {
   return 0;
 }
 
+static void drop_op_graphs(fpb_handle* h);
+
 int fpb_comm_init(fpb_handle* h, const unsigned char id_in[128], int nranks, int rank) {
   if (!h || !id_in) FPB_FAIL(h, "null argument");
   if (nranks < 1 || rank < 0 || rank >= nranks) FPB_FAIL(h, "invalid rank / nranks");
@@ -1646,6 +1684,59 @@ int fpb_comm_init(fpb_handle* h, const unsigned char id_in[128], int nranks, int
                     (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
   h->nranks = nranks;
   h->rank = rank;
+  drop_op_graphs(h);
+  return peer_setup_ipc(h);
+}
+
+// graphs captured before the communicator existed do not contain the shard sum
+static void drop_op_graphs(fpb_handle* h) {
+  for (auto& kv : h->op_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->op_graphs.clear();
+}
+
+// 0 = single shard, 1 = ncclAllReduce, 2 = peer-memory kernel (fpb_peer.cuh)
+int fpb_comm_kind(const fpb_handle* h) {
+  if (!h) return 0;
+  return h->P.ok ? 2 : h->comm ? 1 : 0;
+}
+
+// Shards held by handles of this process (one GPU or several with peer access): handle i becomes
+// rank i of n; the shard sum runs over plain device pointers.  Calls on the n handles must be
+// issued concurrently (one host thread per handle) or at least all enqueued before any is waited
+// for -- each rank's kernel waits for the others.
+int fpb_comm_link_local(fpb_handle** hs, int n) {
+  if (!hs || n < 1 || n > fpb::kPeerMax) FPB_FAIL((fpb_handle*)nullptr, "invalid handle list");
+  for (int i = 0; i < n; i++) {
+    if (!hs[i]) FPB_FAIL((fpb_handle*)nullptr, "null handle");
+    if (hs[i]->comm || hs[i]->P.ok) FPB_FAIL(hs[i], "handle already has a communicator");
+    if (hs[i]->n != hs[0]->n) FPB_FAIL(hs[i], "shards must have the same number of individuals");
+  }
+  for (int i = 0; i < n; i++) {
+    FPB_CUDA(hs[i], cudaSetDevice(hs[i]->device));
+    for (int j = 0; j < n; j++)
+      if (hs[j]->device != hs[i]->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, hs[i]->device, hs[j]->device);
+        if (!can) FPB_FAIL(hs[i], "no peer access between the devices of the shards");
+        cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          FPB_FAIL(hs[i], "cudaDeviceEnablePeerAccess failed");
+        cudaGetLastError();
+      }
+    if (peer_alloc(hs[i])) return 1;
+  }
+  for (int i = 0; i < n; i++) {
+    fpb_handle::Peer& P = hs[i]->P;
+    for (int g = 0; g < n; g++)
+      peer_slot(P.view, g, static_cast<unsigned char*>(hs[g]->P.region), P.cap);
+    P.view.rank = i;
+    P.view.world = n;
+    P.ok = true;
+    hs[i]->nranks = n;
+    hs[i]->rank = i;
+    drop_op_graphs(hs[i]);
+  }
   return 0;
 }
 

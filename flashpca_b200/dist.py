@@ -46,3 +46,41 @@ def attach_nccl(op, world: int, rank: int) -> None:
     dist.broadcast(t, src=0)
     uid = t.cpu().numpy()
     _lib.check(lib.fpb_comm_init(op.h, uid.ctypes.data, world, rank), op.h)
+
+
+def comm_kind(op) -> str:
+    """How the handle sums its shards: 'none', 'nccl' (ncclAllReduce) or 'peer' (one kernel over
+    NVLink peer memory, fused with the op's finalize step; csrc/fpb_peer.cuh)."""
+    from . import _lib
+    return ("none", "nccl", "peer")[int(_lib.load().fpb_comm_kind(op.h))]
+
+
+def link_local(ops) -> None:
+    """Shards held by operators of THIS process (one GPU, or GPUs with peer access) become ranks
+    0..n-1; no NCCL.  Calls on the linked operators must run concurrently, one thread each
+    (run_ranks): every rank's kernel waits for the others."""
+    from . import _lib
+    lib = _lib.load()
+    arr = (ctypes.c_void_p * len(ops))(*[op.h for op in ops])
+    _lib.check(lib.fpb_comm_link_local(arr, len(ops)), ops[0].h)
+
+
+def run_ranks(ops, fn):
+    """fn(op) on one thread per linked operator (ctypes calls release the GIL); results by rank."""
+    import threading
+    out, exc = [None] * len(ops), [None] * len(ops)
+
+    def work(i):
+        try:
+            out[i] = fn(ops[i])
+        except BaseException as e:  # noqa: BLE001
+            exc[i] = e
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(ops))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in exc:
+        if e is not None:
+            raise e
+    return out

@@ -150,6 +150,16 @@ int fpb_sync(fpb_handle *h);
  * distributed by the host program (bench.py uses torch.distributed). */
 int fpb_comm_unique_id(unsigned char id_out[128]);
 int fpb_comm_init(fpb_handle *h, const unsigned char id[128], int nranks, int rank);
+/* The shard sum itself: fpb_comm_init also maps one exchange region per rank into every other
+ * rank (CUDA IPC, handles exchanged over the new communicator); when that works the sum runs as
+ * one kernel over NVLink peer memory, fused with the last step of the op (fixed summation order,
+ * bit-identical on every rank), else as ncclAllReduce.  fpb_comm_kind: 0 = single shard,
+ * 1 = ncclAllReduce, 2 = peer-memory kernel.  FPB_PEER=0 keeps NCCL.
+ * fpb_comm_link_local links n handles of ONE process (shards on one GPU, or on GPUs with peer
+ * access) as ranks 0..n-1 without NCCL; calls on the n handles must be issued concurrently
+ * (one host thread per handle): each rank's kernel waits for the others. */
+int fpb_comm_kind(const fpb_handle *h);
+int fpb_comm_link_local(fpb_handle **handles, int n);
 
 /* ---- whole solve: RandomPCA::pca_fast(Data&, ...) (randompca.cpp:168-218) ----
  * Implicitly restarted Lanczos with the schedule of Spectra 0.8.1

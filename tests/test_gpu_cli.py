@@ -170,16 +170,21 @@ def test_eigen_typed_operator_surface_runs(tmp_path):
     assert "max abs difference: 0" in out.stdout
 
 
-def test_nccl_sharded_two_gpus():
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_nccl_sharded_two_gpus(peer):
+    """SNP-sharded op and solve on 2 GPUs, one process each: with the peer-memory shard sum
+    (csrc/fpb_peer.cuh over CUDA IPC; FPB_PEER=1, the default) and with ncclAllReduce (FPB_PEER=0)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = os.path.join(ROOT, "tests", "_nccl_shard_worker.py")
+    env = dict(os.environ, FPB_PEER=peer, FPB_PEER_TIMEOUT_S="20")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                           "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
-                          "29617", script], capture_output=True, text=True, timeout=180)
+                          "29617", script], capture_output=True, text=True, timeout=180, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "NCCL_SHARD_OK" in out.stdout
+    assert ("shard sum: peer" if peer == "1" else "shard sum: nccl") in out.stdout
 
 
 @pytest.mark.parametrize("mode,stand,divisor", [("plink", 3, 2), ("plink", 2, 1), ("matrix", 3, 2),
