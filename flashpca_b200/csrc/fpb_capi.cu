@@ -132,6 +132,7 @@ struct fpb_handle {
   uint64_t *d_seg_s = nullptr, *d_seg_i = nullptr;
   uint16_t *d_col16_s = nullptr, *d_col16_i = nullptr;
   uint32_t gtiles_s = 0, gtiles_i = 0;
+  uint32_t gather_sms = 0;  // > 0: k_sell_gather_p on that many dedicated SMs
   uint4* d_slices = nullptr;
   double* d_part = nullptr;
   double *d_a = nullptr, *d_corr = nullptr;
@@ -219,6 +220,7 @@ struct fpb_handle {
     void* mapped[fpb::kPeerMax] = {};           // IPC mappings of the other ranks' regions
     fpb::PeerView view = {};
     uint64_t cap = 0;                           // doubles per exchange
+    uint32_t grid = 0;                          // CTAs of the exchange kernel (same on every rank)
     bool fuse = false;                          // the op in flight may sum inside its finalize kernel
     bool summed = false;                        // ... and did
     bool used = false;
@@ -748,6 +750,12 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
     FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_sell_gather,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      fpb::kGatherSmem));
+    FPB_CUDA(h, cudaFuncSetAttribute(fpb::k_sell_gather_p,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fpb::kTmaSmemBytes));
+    // FPB_GATHER_SMS = n: the single-vector op's gathers run on n dedicated SMs beside the
+    // contraction kernel (0: on all SMs in front of it)
+    if (const char* g = getenv("FPB_GATHER_SMS")) h->gather_sms = std::max(0, atoi(g));
   }
   FPB_CUDA(h, cudaStreamSynchronize(h->stream));
   FPB_CUDA(h, cudaGetLastError());
@@ -932,10 +940,17 @@ void gather_launch(fpb_handle* h, bool by_snp, const double* vec) {
   uint32_t chunks = std::max<uint32_t>(1, (4u * h->sm_count) / ntiles);
   uint32_t blocks_per_cta = (nblk + chunks - 1) / chunks;
   chunks = (nblk + blocks_per_cta - 1) / blocks_per_cta;
-  dim3 grid(ntiles, chunks);
-  fpb::k_sell_gather<<<grid, fpb::kGatherThreads, fpb::kGatherSmem, h->side>>>(
-      by_snp ? h->d_seg_s : h->d_seg_i, by_snp ? h->d_col16_s : h->d_col16_i, vec, veclen, nrows,
-      nblk, blocks_per_cta, by_snp ? h->d_mx : h->d_mc);
+  if (h->gather_sms > 0) {
+    // a few dedicated SMs next to the contraction kernel instead of all SMs in front of it
+    fpb::k_sell_gather_p<<<h->gather_sms, fpb::kGatherThreadsP, fpb::kTmaSmemBytes, h->side>>>(
+        by_snp ? h->d_seg_s : h->d_seg_i, by_snp ? h->d_col16_s : h->d_col16_i, vec, veclen, nrows,
+        nblk, blocks_per_cta, chunks, ntiles * chunks, by_snp ? h->d_mx : h->d_mc);
+  } else {
+    dim3 grid(ntiles, chunks);
+    fpb::k_sell_gather<<<grid, fpb::kGatherThreads, fpb::kGatherSmem, h->side>>>(
+        by_snp ? h->d_seg_s : h->d_seg_i, by_snp ? h->d_col16_s : h->d_col16_i, vec, veclen, nrows,
+        nblk, blocks_per_cta, by_snp ? h->d_mx : h->d_mc);
+  }
   cudaEventRecord(h->ev_join, h->side);
   h->launches++;
 }
@@ -1712,6 +1727,10 @@ int fpb_comm_link_local(fpb_handle** hs, int n) {
     if (hs[i]->comm || hs[i]->P.ok) FPB_FAIL(hs[i], "handle already has a communicator");
     if (hs[i]->n != hs[0]->n) FPB_FAIL(hs[i], "shards must have the same number of individuals");
   }
+  bool shared_device = false;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < i; j++) shared_device |= hs[i]->device == hs[j]->device;
+  if (shared_device && n > 4) FPB_FAIL(hs[0], "at most 4 linked shards may share a GPU");
   for (int i = 0; i < n; i++) {
     FPB_CUDA(hs[i], cudaSetDevice(hs[i]->device));
     for (int j = 0; j < n; j++)
@@ -1732,6 +1751,7 @@ int fpb_comm_link_local(fpb_handle** hs, int n) {
       peer_slot(P.view, g, static_cast<unsigned char*>(hs[g]->P.region), P.cap);
     P.view.rank = i;
     P.view.world = n;
+    P.grid = shared_device ? fpb::kPeerCtasShared : fpb::kPeerCtas;
     P.ok = true;
     hs[i]->nranks = n;
     hs[i]->rank = i;

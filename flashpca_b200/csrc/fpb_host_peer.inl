@@ -115,13 +115,12 @@ int peer_setup_ipc(fpb_handle* h) {
   }
   P.view.rank = h->rank;
   P.view.world = W;
+  P.grid = fpb::kPeerCtas;
   P.ok = true;
   return 0;
 }
 
-uint32_t peer_grid(const fpb_handle* h) {
-  return (uint32_t)std::min<int>(fpb::kPeerCtas, h->sm_count);
-}
+uint32_t peer_grid(const fpb_handle* h) { return h->P.grid; }
 
 // in-place sum of d_buf[count] over the ranks
 int peer_allreduce(fpb_handle* h, double* d_buf, size_t count) {

@@ -1482,32 +1482,31 @@ k_sell_fill(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ co
   }
 }
 
-// grid (ntiles, chunks of row blocks); partial[t * nrows + r] = sum over tile t of row r
-__global__ void __launch_bounds__(kGatherThreads, 2)
-k_sell_gather(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ col16,
-              const double* __restrict__ vec, uint64_t veclen, uint64_t nrows, uint32_t nblk,
-              uint32_t blocks_per_cta, double* __restrict__ partial) {
-  extern __shared__ double xs[];
-  const uint32_t t = blockIdx.x;
+// tile t of the gathered vector -> shared memory (THREADS threads; caller synchronises)
+template <int THREADS>
+__device__ __forceinline__ void sell_load_tile(double* xs, const double* __restrict__ vec,
+                                               uint64_t veclen, uint32_t t) {
   const uint64_t base = (uint64_t)t * kGatherTile;
-  {
-    constexpr int PER = kGatherTile / kGatherThreads;  // 24 loads per thread, issued together
-    double tmp[PER];
+  constexpr int PER = kGatherTile / THREADS;  // loads per thread, issued together
+  double tmp[PER];
 #pragma unroll
-    for (int m = 0; m < PER; m++) {
-      const uint32_t i = threadIdx.x + m * kGatherThreads;
-      tmp[m] = (base + i < veclen) ? vec[base + i] : 0.0;
-    }
-#pragma unroll
-    for (int m = 0; m < PER; m++) xs[threadIdx.x + m * kGatherThreads] = tmp[m];
-    if (threadIdx.x < kGatherPad) xs[kGatherTile + threadIdx.x] = 0.0;
+  for (int m = 0; m < PER; m++) {
+    const uint32_t i = threadIdx.x + m * THREADS;
+    tmp[m] = (base + i < veclen) ? vec[base + i] : 0.0;
   }
-  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < PER; m++) xs[threadIdx.x + m * THREADS] = tmp[m];
+  if (threadIdx.x < kGatherPad) xs[kGatherTile + threadIdx.x] = 0.0;
+}
+
+// row blocks [b0, b1) of tile t: out[r] = sum of the row's entries in the tile
+template <int THREADS>
+__device__ __forceinline__ void sell_walk_blocks(const double* xs, const uint64_t* __restrict__ bo,
+                                                 const uint16_t* __restrict__ col16, uint32_t b0,
+                                                 uint32_t b1, uint64_t nrows,
+                                                 double* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t b0 = blockIdx.y * blocks_per_cta, b1 = min(nblk, b0 + blocks_per_cta);
-  const uint64_t* bo = blkoff + (uint64_t)t * nblk;
-  double* out = partial + (uint64_t)t * nrows;
-  constexpr int NW = kGatherThreads / 32;
+  constexpr int NW = THREADS / 32;
   uint32_t b = b0 + warp;
   uint64_t o = 0, onext = 0;
   if (b < b1) {
@@ -1550,6 +1549,49 @@ k_sell_gather(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ 
     if (r < nrows) out[r] = (s0 + s1) + (s2 + s3);
     o = o2;
     onext = o2next;
+  }
+}
+
+// grid (ntiles, chunks of row blocks); partial[t * nrows + r] = sum over tile t of row r
+__global__ void __launch_bounds__(kGatherThreads, 2)
+k_sell_gather(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ col16,
+              const double* __restrict__ vec, uint64_t veclen, uint64_t nrows, uint32_t nblk,
+              uint32_t blocks_per_cta, double* __restrict__ partial) {
+  extern __shared__ double xs[];
+  const uint32_t t = blockIdx.x;
+  sell_load_tile<kGatherThreads>(xs, vec, veclen, t);
+  __syncthreads();
+  const uint32_t b0 = blockIdx.y * blocks_per_cta, b1 = min(nblk, b0 + blocks_per_cta);
+  sell_walk_blocks<kGatherThreads>(xs, blkoff + (uint64_t)t * nblk, col16, b0, b1, nrows,
+                                   partial + (uint64_t)t * nrows);
+}
+
+// The same sums on a few dedicated SMs: `gridDim.x` CTAs of 1024 threads (launched with the SM's
+// whole shared memory, so nothing shares the SM) walk contiguous ranges of the (tile, chunk)
+// items while the contraction kernel -- whose CTAs cannot share an SM with a gather CTA -- runs on
+// all the others.  The op's critical path then holds no gather at all; same summation order as
+// k_sell_gather (bit-identical results).
+constexpr int kGatherThreadsP = 1024;
+__global__ void __launch_bounds__(kGatherThreadsP, 1)
+k_sell_gather_p(const uint64_t* __restrict__ blkoff, const uint16_t* __restrict__ col16,
+                const double* __restrict__ vec, uint64_t veclen, uint64_t nrows, uint32_t nblk,
+                uint32_t blocks_per_item, uint32_t chunks, uint32_t nitems,
+                double* __restrict__ partial) {
+  extern __shared__ double xs[];
+  const uint32_t per = (nitems + gridDim.x - 1) / gridDim.x;
+  const uint32_t i0 = blockIdx.x * per, i1 = min(nitems, i0 + per);
+  uint32_t cur = ~0u;
+  for (uint32_t item = i0; item < i1; item++) {
+    const uint32_t t = item / chunks, c = item - t * chunks;
+    if (t != cur) {
+      __syncthreads();  // the previous item's reads of the tile
+      sell_load_tile<kGatherThreadsP>(xs, vec, veclen, t);
+      __syncthreads();
+      cur = t;
+    }
+    const uint32_t b0 = c * blocks_per_item, b1 = min(nblk, b0 + blocks_per_item);
+    sell_walk_blocks<kGatherThreadsP>(xs, blkoff + (uint64_t)t * nblk, col16, b0, b1, nrows,
+                                      partial + (uint64_t)t * nrows);
   }
 }
 

@@ -17,7 +17,7 @@
 // Every element is summed by exactly one rank in a fixed order, so all ranks hold bit-identical y
 // (the replicated Lanczos drivers must take identical decisions) and the result does not depend on
 // timing.  A CTA only ever waits for the CTA of the same index on the other GPUs, so there is no
-// dependency between the CTAs of one GPU; the grid (64 CTAs) is always resident.  Flags carry a per-CTA epoch that the kernel advances itself (device memory), so
+// dependency between the CTAs of one GPU; the grid (128 CTAs, one per SM) is always resident.  Flags carry a per-CTA epoch that the kernel advances itself (device memory), so
 // the launch is a plain kernel node and the whole op replays as a CUDA graph.  Every wait is bounded
 // (FPB_PEER_TIMEOUT_S, default 60 s: ranks may be skewed by host work between two ops) and reports
 // through the handle's error word instead of hanging the GPU.
@@ -30,9 +30,10 @@
 namespace fpb {
 
 constexpr int kPeerMax = 8;          // GPUs of one box
-constexpr int kPeerCtas = 64;        // CTAs of the exchange kernel (all resident, also when the shards
-                                     // of a test share one GPU: 3 ranks x 64 CTAs on 148 SMs)
-constexpr int kPeerThreads = 512;
+constexpr int kPeerCtas = 128;       // CTAs of the exchange kernel between GPUs: one per SM, all resident
+constexpr int kPeerCtasShared = 32;  // ... when the linked shards share one GPU (tests): the grids of
+                                     // up to 4 ranks must be resident together
+constexpr int kPeerThreads = 1024;
 
 struct PeerView {
   double* loc[kPeerMax];      // exchange buffers (partial sums), by rank; [rank] is local
@@ -88,7 +89,7 @@ __device__ __forceinline__ bool peer_barrier(const PeerView& pv, uint32_t* const
 
 // FUSED: phase 0 is k_finalize_prod (part / sc_ab / mcv as there); else phase 0 copies src.
 template <bool FUSED>
-__global__ void __launch_bounds__(kPeerThreads, 2)
+__global__ void __launch_bounds__(kPeerThreads, 1)
 k_allreduce_peer(PeerView pv, const double* __restrict__ src, const double* __restrict__ part,
                  uint32_t nsplits, uint64_t stride, const VecScale* __restrict__ sc_ab,
                  const double* __restrict__ mcv, uint32_t mc_tiles, uint64_t mc_stride,
@@ -111,10 +112,13 @@ k_allreduce_peer(PeerView pv, const double* __restrict__ src, const double* __re
       double v;
       if (FUSED) {
         double f = 0.0;
+#pragma unroll 4
         for (uint32_t s = 0; s < nsplits; s++) f += part[(uint64_t)s * stride + i];
         double mc = 0.0;
-        if (mcv)
+        if (mcv) {
+#pragma unroll 4
           for (uint32_t tt = 0; tt < mc_tiles; tt++) mc += mcv[(uint64_t)tt * mc_stride + i];
+        }
         v = f * delta - sumb + mc;
       } else {
         v = src[i];
