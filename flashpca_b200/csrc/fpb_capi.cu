@@ -133,6 +133,8 @@ struct fpb_handle {
   uint16_t *d_col16_s = nullptr, *d_col16_i = nullptr;
   uint32_t gtiles_s = 0, gtiles_i = 0;
   uint32_t gather_sms = 0;  // > 0: k_sell_gather_p on that many dedicated SMs
+  // first SNP row of the window the first half leaves in L2 for the second half (evict_last)
+  uint32_t l2_keep_row = 0xFFFFFFFFu;
   uint4* d_slices = nullptr;
   double* d_part = nullptr;
   double *d_a = nullptr, *d_corr = nullptr;
@@ -217,6 +219,7 @@ struct fpb_handle {
   struct Peer {
     bool ok = false;
     void* region = nullptr;                     // this rank's exchange region
+    uint32_t* h_err = nullptr;                  // watchdog word (mapped pinned host memory)
     void* mapped[fpb::kPeerMax] = {};           // IPC mappings of the other ranks' regions
     fpb::PeerView view = {};
     uint64_t cap = 0;                           // doubles per exchange
@@ -686,6 +689,16 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
         override_splits("FPB_DEBUG_SPLITS2", h->ttiles, &h->psplits_t, &h->ptps_t);
       }
     }
+    if (h->single_copy) {
+      // L2 window: the last SNP rows read by the first half stay in L2 (evict_last) and the second
+      // half finds them there.  FPB_L2_KEEP_MB sets its size (0 = off).
+      const char* kv = getenv("FPB_L2_KEEP_MB");
+      const double keep_mb = kv ? atof(kv) : 0.0;
+      const uint32_t ntile_s = (uint32_t)((h->nsnps + fpb::kTmaRows - 1) / fpb::kTmaRows);
+      const uint64_t tile_bytes = (uint64_t)h->pitch_s * fpb::kTmaRows;
+      const uint32_t keep_tiles = (uint32_t)std::min<uint64_t>(ntile_s, (uint64_t)(keep_mb * 1e6) / tile_bytes);
+      h->l2_keep_row = keep_tiles ? (ntile_s - keep_tiles) * fpb::kTmaRows : 0xFFFFFFFFu;
+    }
     if (h->use_tma) {
       if (make_tensor_map(h, h->d_gs, h->pitch_s, h->nsnps, &h->tm_s)) return 1;
       if (!h->single_copy && make_tensor_map(h, h->d_gi, h->pitch_i, h->n, &h->tm_i)) return 1;
@@ -900,7 +913,7 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
     fpb::k_imma_gemv_tma_p<<<std::min<uint32_t>((uint32_t)h->sm_count, nitems),
                              (fpb::kTmaConsumerWarps + 1) * 32, fpb::kTmaSmemBytes, h->stream>>>(
         h->tm_s, rows, h->d_slices, h->nstages_s, h->psps_s, h->psplits_s, nitems, h->d_part,
-        h->part_stride);
+        h->part_stride, h->l2_keep_row);
     return h->psplits_s;
   }
   if (h->use_tma) {
@@ -913,7 +926,8 @@ uint32_t imma_contract(fpb_handle* h, bool snp_major, const double* d_v, uint64_
     static const int smem_bytes = getenv("FPB_DEBUG_SMEM_MIN") ? fpb::kTmaSmemUsed : fpb::kTmaSmemBytes;
     fpb::k_imma_gemv_tma<<<grid, (fpb::kTmaConsumerWarps + 1) * 32, smem_bytes,
                            h->stream>>>(snp_major ? h->tm_s : h->tm_i, rows, h->d_slices, nstages,
-                                        sps, h->d_part, h->part_stride);
+                                        sps, h->d_part, h->part_stride,
+                                        snp_major ? h->l2_keep_row : 0xFFFFFFFFu);
     return splits;
   }
   const uint32_t splits = snp_major ? h->splits_s : h->splits_i;

@@ -1,7 +1,7 @@
 // Host side of the peer-memory shard sum (fpb_peer.cuh); textual include of fpb_capi.cu (inside its
 // anonymous namespace).
 //
-// Every rank allocates one region  [loc: cap doubles][res: cap doubles][flag_a][flag_b][epoch][err]
+// Every rank allocates one region  [loc: cap doubles][res: cap doubles][flag_a][flag_b][epoch]
 // and maps the regions of the other ranks: through CUDA IPC handles when the ranks are processes
 // (fpb_comm_init: the 64-byte handles travel over the NCCL communicator that was just created), or
 // by plain pointers when they are handles of one process (fpb_comm_link_local: the shards of a
@@ -32,7 +32,11 @@ int peer_alloc(fpb_handle* h) {
   unsigned char* base = static_cast<unsigned char*>(P.region);
   unsigned char* tail = base + 2 * sizeof(double) * P.cap + 2 * peer_flags_bytes();
   P.view.epoch = reinterpret_cast<uint32_t*>(tail);
-  P.view.err = reinterpret_cast<uint32_t*>(tail + sizeof(uint32_t) * fpb::kPeerCtas);
+  // the watchdog word lives in mapped pinned host memory: the host reads it after any sync
+  // without another copy on the op's critical path
+  FPB_CUDA(h, cudaHostAlloc(&P.h_err, sizeof(uint32_t), cudaHostAllocMapped));
+  *P.h_err = 0;
+  FPB_CUDA(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&P.view.err), P.h_err, 0));
   const char* to = getenv("FPB_PEER_TIMEOUT_S");
   P.view.timeout_ns = (unsigned long long)((to && atof(to) > 0 ? atof(to) : 60.0) * 1e9);
   return 0;
@@ -43,6 +47,7 @@ void peer_release(fpb_handle* h) {
   for (int g = 0; g < fpb::kPeerMax; g++)
     if (P.mapped[g]) cudaIpcCloseMemHandle(P.mapped[g]);
   cudaFree(P.region);
+  if (P.h_err) cudaFreeHost(P.h_err);
   P = fpb_handle::Peer();
 }
 
@@ -146,15 +151,13 @@ void peer_finalize_prod(fpb_handle* h, uint32_t nsplits, double* d_y) {
   P.summed = true;
 }
 
-int check_peer(fpb_handle* h) {
+int check_peer(fpb_handle* h) {  // after a synchronisation of the stream
   fpb_handle::Peer& P = h->P;
   if (!P.ok || !P.used) return 0;
   P.used = false;
-  uint32_t code = 0;
-  FPB_CUDA(h, cudaMemcpyAsync(&code, P.view.err, sizeof(code), cudaMemcpyDeviceToHost, h->stream));
-  FPB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const uint32_t code = *reinterpret_cast<volatile uint32_t*>(P.h_err);
   if (code) {
-    cudaMemsetAsync(P.view.err, 0, sizeof(code), h->stream);
+    *P.h_err = 0;
     char buf[80];
     snprintf(buf, sizeof buf, "peer-memory shard sum: wait for a peer timed out (code %x)", code);
     FPB_FAIL(h, buf);

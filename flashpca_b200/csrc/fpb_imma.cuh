@@ -461,7 +461,7 @@ struct alignas(64) TmaDesc {  // CUtensorMap is an opaque 128-byte, 64-byte alig
 __global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
 k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* __restrict__ S,
                 uint32_t nstages, uint32_t stages_per_split, double* __restrict__ out,
-                uint64_t out_stride) {
+                uint64_t out_stride, uint32_t keep_row = 0xFFFFFFFFu) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B: 1 KB aligned
   const uint32_t bars = base + kTmaStages * kTmaStageBytes;       // full[], then empty[]
@@ -492,8 +492,10 @@ k_imma_gemv_tma(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* _
         if (round > 0) mbar_wait(empty, (round - 1) & 1);
         const uint32_t dst = base + slot * kTmaStageBytes;
         mbar_expect_tx(full, kTmaStageBytes);
+        // rows from keep_row on stay in L2 for the second half of the op (evict_last); the rest
+        // of the matrix streams through (evict_first)
         tma_load_2d(dst, &tmap, (int)((s_begin + it) * kTmaStageCols), (int)row0, full,
-                    pol_stream);
+                    row0 >= keep_row ? pol_keep : pol_stream);
         bulk_load(dst + kTmaTileBytes, S + (uint64_t)(s_begin + it) * (kTmaSliceBytes / 16),
                   kTmaSliceBytes, full, pol_keep);
       }
@@ -1160,7 +1162,7 @@ k_imma_gemv_tma_tw(const __grid_constant__ TmaDesc tmap /* box 128 B x 128 rows 
 __global__ void __launch_bounds__((kTmaConsumerWarps + 1) * 32, 1)
 k_imma_gemv_tma_p(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4* __restrict__ S,
                   uint32_t nstages, uint32_t stages_per_split, uint32_t nsplits, uint32_t nitems,
-                  double* __restrict__ out, uint64_t out_stride) {
+                  double* __restrict__ out, uint64_t out_stride, uint32_t keep_row = 0xFFFFFFFFu) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + kTmaStages * kTmaStageBytes;
@@ -1189,7 +1191,8 @@ k_imma_gemv_tma_p(const __grid_constant__ TmaDesc tmap, uint32_t R, const uint4*
           if (round > 0) mbar_wait(empty, (round - 1) & 1);
           const uint32_t dst = base + slot * kTmaStageBytes;
           mbar_expect_tx(full, kTmaStageBytes);
-          tma_load_2d(dst, &tmap, (int)(st * kTmaStageCols), (int)(rt * kTmaRows), full, pol_stream);
+          tma_load_2d(dst, &tmap, (int)(st * kTmaStageCols), (int)(rt * kTmaRows), full,
+                      rt * kTmaRows >= keep_row ? pol_keep : pol_stream);
           bulk_load(dst + kTmaTileBytes, S + (uint64_t)st * (kTmaSliceBytes / 16), kTmaSliceBytes,
                     full, pol_keep);
           if (++slot == kTmaStages) {

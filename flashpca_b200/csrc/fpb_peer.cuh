@@ -41,7 +41,7 @@ struct PeerView {
   uint32_t* flag_a[kPeerMax]; // flag words of each rank: [cta * kPeerMax + source rank]
   uint32_t* flag_b[kPeerMax];
   uint32_t* epoch;            // local, one word per CTA
-  uint32_t* err;              // local watchdog word
+  uint32_t* err;              // watchdog word (mapped host memory)
   unsigned long long timeout_ns;  // bound of every wait
   int rank, world;
 };
@@ -77,7 +77,8 @@ __device__ __forceinline__ bool peer_barrier(const PeerView& pv, uint32_t* const
       const unsigned long long t0 = peer_now();
       while ((int32_t)(peer_ld_acquire(mine) - e) < 0) {
         if (peer_now() - t0 > pv.timeout_ns) {
-          atomicExch(pv.err, 0x50000000u | (blockIdx.x << 8) | g);
+          *reinterpret_cast<volatile uint32_t*>(pv.err) = 0x50000000u | (blockIdx.x << 8) | g;
+          __threadfence_system();
           ok = false;
           break;
         }
