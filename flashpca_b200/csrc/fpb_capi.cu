@@ -23,6 +23,7 @@
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -1202,23 +1203,55 @@ int fpb_create_from_file(fpb_handle** out, const char* bed_path, uint64_t n, uin
   int rc = alloc_common(h, n, snp_count, stand_method, device);
   if (!rc) {
     rc = [&]() -> int {
-      // double-buffered pinned staging, 32 MiB slabs of whole SNP rows
-      uint64_t rows_per_slab = std::max<uint64_t>(1, (32ull << 20) / np);
+      // double-buffered pinned staging, 64 MiB slabs of whole SNP rows; a slab is read by several
+      // threads at once (pread on disjoint row ranges: one thread copies ~3 GB/s out of the page
+      // cache, the H2D copy it feeds runs at 55 GB/s), and the copy of slab b overlaps the read of
+      // slab b + 1.  FPB_READ_THREADS overrides the thread count (default min(8, cores)).
+      uint64_t rows_per_slab = std::max<uint64_t>(1, (64ull << 20) / np);
+      rows_per_slab = std::min<uint64_t>(rows_per_slab, std::max<uint64_t>(1, snp_count));
+      const char* rt = getenv("FPB_READ_THREADS");
+      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      const unsigned nthr = rt && atoi(rt) > 0 ? (unsigned)atoi(rt) : std::min(8u, hw);
+      const int fd = fileno(f);
       unsigned char* pin[2] = {nullptr, nullptr};
       cudaEvent_t ev[2];
       for (int b = 0; b < 2; b++) {
         FPB_CUDA(h, cudaMallocHost(&pin[b], rows_per_slab * np));
         FPB_CUDA(h, cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
       }
-      fseeko(f, (off_t)(3 + np * snp_begin), SEEK_SET);
+      const uint64_t file_off = 3 + np * snp_begin;
+      auto read_range = [&](unsigned char* dst, uint64_t off, uint64_t len) -> bool {
+        while (len) {
+          const ssize_t got = pread(fd, dst, len, (off_t)off);
+          if (got <= 0) {
+            if (got < 0 && errno == EINTR) continue;
+            return false;
+          }
+          dst += got;
+          off += (uint64_t)got;
+          len -= (uint64_t)got;
+        }
+        return true;
+      };
       int b = 0;
       int failed = 0;
       for (uint64_t r = 0; r < snp_count && !failed; r += rows_per_slab, b ^= 1) {
-        uint64_t rows = std::min(rows_per_slab, snp_count - r);
+        const uint64_t rows = std::min(rows_per_slab, snp_count - r);
+        const uint64_t bytes = rows * np, off0 = file_off + r * np;
         cudaEventSynchronize(ev[b]);
-        if (fread(pin[b], 1, rows * np, f) != rows * np) {
+        const unsigned nt = (unsigned)std::min<uint64_t>(nthr, std::max<uint64_t>(1, bytes >> 20));
+        std::vector<char> okv(nt, 1);
+        auto part = [&](unsigned i) {
+          const uint64_t lo = bytes * i / nt, hi = bytes * (i + 1) / nt;
+          okv[i] = read_range(pin[b] + lo, off0 + lo, hi - lo) ? 1 : 0;
+        };
+        std::vector<std::thread> pool;
+        for (unsigned i = 1; i < nt; i++) pool.emplace_back(part, i);
+        part(0);
+        for (auto& th : pool) th.join();
+        for (unsigned i = 0; i < nt; i++) failed |= !okv[i];
+        if (failed) {
           h->err = std::string("[Data::read_bed] Error reading file ") + bed_path;
-          failed = 1;
           break;
         }
         if (cudaMemcpy2DAsync(h->d_gs + r * h->pitch_s, h->pitch_s, pin[b], np, np, rows,
