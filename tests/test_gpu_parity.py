@@ -193,7 +193,7 @@ def test_tensor_path_is_deterministic_and_default(native_lib, monkeypatch):
     assert np.isnan(op.perform_op(np.full(n, np.nan))).all()
 
 
-@pytest.mark.parametrize("variant", ["tma", "tma2", "ldg", "wide", "narrow"])
+@pytest.mark.parametrize("variant", ["tma", "tma2", "ldg", "wide", "narrow", "gather_sms", "l2_keep"])
 def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
     """FPB_GEMV selects the contraction kernels: default single-copy TMA pipeline
     (k_imma_gemv_tma + k_imma_gemv_tma_t), two-copy TMA (tma2) and the register-staged
@@ -213,11 +213,17 @@ def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
     elif variant == "narrow":   # one-shot 128-byte stripe grids
         monkeypatch.setenv("FPB_P2WIDE", "0")
         monkeypatch.setenv("FPB_PERSIST", "0")
+    elif variant == "gather_sms":   # missing-genotype gathers on 3 dedicated SMs (k_sell_gather_p)
+        monkeypatch.setenv("FPB_GATHER_SMS", "3")
+    elif variant == "l2_keep":      # first half leaves its last SNP rows in L2 (evict_last)
+        monkeypatch.setenv("FPB_L2_KEEP_MB", "1")
     else:
         monkeypatch.setenv("FPB_GEMV", variant)
     op = _mk(payload, n, p)
     y1 = op.perform_op(x)
     assert _relerr(y1, y0) <= 1e-13
+    if variant in ("gather_sms", "l2_keep"):   # same kernels' arithmetic, same summation order
+        assert np.array_equal(y1, y0)
     assert _relerr(op.crossprod(x), t0) <= 1e-13
     assert _relerr(op.prod(v), z0) <= 1e-13
     assert np.array_equal(op.perform_op(x), y1)
