@@ -692,9 +692,11 @@ int finish_create(fpb_handle* h, const double* preloaded_meansd) {
     }
     if (h->single_copy) {
       // L2 window: the last SNP rows read by the first half stay in L2 (evict_last) and the second
-      // half finds them there.  FPB_L2_KEEP_MB sets its size (0 = off).
+      // half finds them there.  Measured (profiles/r02_l2_keep_window_sweep.txt): -3 % per op at
+      // 10k x 100k (250 MB) with 24-64 MB, nothing at 1.5 GB and above -- on for matrices below
+      // 1 GB.  FPB_L2_KEEP_MB overrides the size (0 = off).
       const char* kv = getenv("FPB_L2_KEEP_MB");
-      const double keep_mb = kv ? atof(kv) : 0.0;
+      const double keep_mb = kv ? atof(kv) : ((double)h->pitch_s * (double)h->nsnps < 1e9 ? 32.0 : 0.0);
       const uint32_t ntile_s = (uint32_t)((h->nsnps + fpb::kTmaRows - 1) / fpb::kTmaRows);
       const uint64_t tile_bytes = (uint64_t)h->pitch_s * fpb::kTmaRows;
       const uint32_t keep_tiles = (uint32_t)std::min<uint64_t>(ntile_s, (uint64_t)(keep_mb * 1e6) / tile_bytes);

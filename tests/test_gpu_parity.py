@@ -193,7 +193,7 @@ def test_tensor_path_is_deterministic_and_default(native_lib, monkeypatch):
     assert np.isnan(op.perform_op(np.full(n, np.nan))).all()
 
 
-@pytest.mark.parametrize("variant", ["tma", "tma2", "ldg", "wide", "narrow", "gather_sms", "l2_keep"])
+@pytest.mark.parametrize("variant", ["tma", "tma2", "ldg", "wide", "narrow", "gather_sms", "l2_keep_off"])
 def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
     """FPB_GEMV selects the contraction kernels: default single-copy TMA pipeline
     (k_imma_gemv_tma + k_imma_gemv_tma_t), two-copy TMA (tma2) and the register-staged
@@ -215,14 +215,14 @@ def test_contraction_kernel_variants_agree(native_lib, monkeypatch, variant):
         monkeypatch.setenv("FPB_PERSIST", "0")
     elif variant == "gather_sms":   # missing-genotype gathers on 3 dedicated SMs (k_sell_gather_p)
         monkeypatch.setenv("FPB_GATHER_SMS", "3")
-    elif variant == "l2_keep":      # first half leaves its last SNP rows in L2 (evict_last)
-        monkeypatch.setenv("FPB_L2_KEEP_MB", "1")
+    elif variant == "l2_keep_off":  # default: the first half leaves its last SNP rows in L2 for the
+        monkeypatch.setenv("FPB_L2_KEEP_MB", "0")   # second (evict_last) when the matrix is small
     else:
         monkeypatch.setenv("FPB_GEMV", variant)
     op = _mk(payload, n, p)
     y1 = op.perform_op(x)
     assert _relerr(y1, y0) <= 1e-13
-    if variant in ("gather_sms", "l2_keep"):   # same kernels' arithmetic, same summation order
+    if variant in ("gather_sms", "l2_keep_off"):   # same kernels' arithmetic, same summation order
         assert np.array_equal(y1, y0)
     assert _relerr(op.crossprod(x), t0) <= 1e-13
     assert _relerr(op.prod(v), z0) <= 1e-13
