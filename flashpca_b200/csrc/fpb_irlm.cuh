@@ -287,6 +287,36 @@ inline void simple_random_vec(std::vector<double>& out, uint64_t n, unsigned lon
   }
 }
 
+inline unsigned long long simple_random_r0(unsigned long seed) {
+  return seed ? (seed & 2147483647UL) : 1UL;
+}
+
+// The same vector on the device: element i is r0 a^(i+1) mod m, so every thread jumps ahead on its
+// own (31 squarings); bit-identical to simple_random_vec.  (The host loop plus the pageable 8 N
+// byte upload cost ~5 ms per solve at N = 500,000: 2 % of a 1-GPU solve, 9 % of an 8-GPU one.)
+__global__ void __launch_bounds__(256)
+k_simple_random(double* __restrict__ out, uint64_t n, unsigned long long r0) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long m = 2147483647ull;
+  unsigned long long e = i + 1, base = 16807ull, acc = r0 % m;
+  while (e) {
+    if (e & 1) acc = (acc * base) % m;
+    base = (base * base) % m;
+    e >>= 1;
+  }
+  out[i] = (double)acc / (double)m - 0.5;
+}
+
+// coefficient vector of a Lanczos step's first pass, built on the device:
+// h = (0, ..., 0, beta_prev, Hii) with Hii = v_i . w read from *hii
+__global__ void k_first_coeffs(double* __restrict__ h, uint32_t m, double beta_prev,
+                               const double* __restrict__ hii) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  h[c] = c + 1 == m ? *hii : (c + 2 == m ? beta_prev : 0.0);
+}
+
 // Eigen-decomposition of a symmetric tridiagonal matrix by implicit-shift QL.
 // d: diagonal (n), e: sub-diagonal (e[i] couples i and i+1; e[n-1] unused),
 // z: n x n column-major, returns eigenvectors in columns.  false on failure.
@@ -429,6 +459,7 @@ class Irlm {
   }
   // fused pass: f = fin - V[:, :m] h (h_host may be null), returns V'f in vf[0..m) and ||f||
   double reorth_pass(uint32_t m, const double* h_host, const double* fin, double* vf);
+  double reorth_first(uint32_t i, double beta_prev, double* vf, double* hii_out);
   void factorize_from(uint32_t from_k, uint32_t to_m);
   void retrieve_ritzpair();
   // d_out (N x nc) = V (N x ncv) * dQ (ncv x nc)
@@ -490,13 +521,13 @@ inline void Irlm::alloc() {
   cudaMalloc(&dW_, sizeof(double) * n_);
   cudaMalloc(&dX_, sizeof(double) * n_);
   cudaMalloc(&dPartial_, sizeof(double) * (size_t)nblocks_ * ncv_);
-  cudaMalloc(&dSmall_, sizeof(double) * (ncv_ + 1));
+  cudaMalloc(&dSmall_, sizeof(double) * (ncv_ + 2));
   cudaMalloc(&dQ_, sizeof(double) * ncv_ * ncv_);
   fused_ = ncv_ <= 48;
   nblocks256_ = (uint32_t)((n_ + 255) / 256);
   cudaMalloc(&dPartial2_, sizeof(double) * (size_t)nblocks256_ * (ncv_ + 1));
   cudaMalloc(&dH_, sizeof(double) * (ncv_ + 1));
-  cudaMallocHost(&hPinned_, sizeof(double) * (ncv_ + 1));
+  cudaMallocHost(&hPinned_, sizeof(double) * (ncv_ + 2));
   cudaMemsetAsync(dV_, 0, sizeof(double) * n_ * ncv_, stream_);
   H_.assign((size_t)ncv_ * ncv_, 0.0);
 }
@@ -535,6 +566,25 @@ inline double Irlm::reorth_pass(uint32_t m, const double* h_host, const double* 
   return sqrt(hPinned_[m]);
 }
 
+// First pass of Lanczos step i without a host round trip for Hii: Hii = v_i . w goes straight
+// into the coefficient vector on the device, f = w - beta v_{i-1} - Hii v_i, V'f and ||f|| follow
+// in the same stream, and one synchronisation returns all of them (same arithmetic as
+// gemv_t + reorth_pass: Hii is the same double either way).
+inline double Irlm::reorth_first(uint32_t i, double beta_prev, double* vf, double* hii_out) {
+  const uint32_t m = i + 1;
+  k_gemv_t_partial<<<nblocks_, 256, 0, stream_>>>(col(i), n_, 1, dW_, n_, dPartial_);
+  k_gemv_t_final<<<1, 256, 0, stream_>>>(dPartial_, nblocks_, 1, dSmall_ + m + 1);
+  k_first_coeffs<<<(m + 63) / 64, 64, 0, stream_>>>(dH_, m, beta_prev, dSmall_ + m + 1);
+  k_fused_reorth<48><<<nblocks256_, 256, 0, stream_>>>(dV_, n_, m, dH_, dW_, dF_, n_, dPartial2_);
+  k_gemv_t_final<<<((m + 1) * 32 + 255) / 256, 256, 0, stream_>>>(dPartial2_, nblocks256_, m + 1,
+                                                                   dSmall_);
+  cudaMemcpyAsync(hPinned_, dSmall_, sizeof(double) * (m + 2), cudaMemcpyDeviceToHost, stream_);
+  cudaStreamSynchronize(stream_);
+  memcpy(vf, hPinned_, sizeof(double) * m);
+  *hii_out = hPinned_[m + 1];
+  return sqrt(hPinned_[m]);
+}
+
 inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
   if (to_m <= from_k) return;
   const double eps = DBL_EPSILON, near0 = DBL_MIN * 10.0;
@@ -543,13 +593,12 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
     for (uint32_t r = 0; r < ncv_; r++) H(r, c) = 0.0;
   for (uint32_t r = from_k; r < ncv_; r++)
     for (uint32_t c = 0; c < from_k; c++) H(r, c) = 0.0;
-  std::vector<double> Vf(ncv_), rnd;
+  std::vector<double> Vf(ncv_);
   for (uint32_t i = from_k; i < to_m; i++) {
     bool restart = false;
     if (beta < near0) {
       // invariant subspace: new random direction orthogonal to V[:, :i]
-      simple_random_vec(rnd, n_, 2UL * i);
-      cudaMemcpyAsync(dF_, rnd.data(), sizeof(double) * n_, cudaMemcpyHostToDevice, stream_);
+      k_simple_random<<<grid1d(256), 256, 0, stream_>>>(dF_, n_, simple_random_r0(2UL * i));
       gemv_t(dV_, i, dF_, Vf.data());
       cudaMemcpyAsync(dSmall_, Vf.data(), sizeof(double) * i, cudaMemcpyHostToDevice, stream_);
       gemv_n_sub(i, dSmall_);
@@ -563,20 +612,21 @@ inline void Irlm::factorize_from(uint32_t from_k, uint32_t to_m) {
     nops_++;
     double tb = now_s();
     double Hii;
-    gemv_t(col(i), 1, dW_, &Hii);
-    double tc = now_s();
+    const uint32_t i1 = i + 1;
+    double tc = tb;
+    if (fused_) {
+      // Hii, f = w - H(i,i-1) v_{i-1} - Hii v_i, V'f and ||f||: one pass over V[:, :i+1], one sync
+      beta = reorth_first(i, restart ? 0.0 : H(i, i - 1), Vf.data(), &Hii);
+      tc = now_s();
+    } else {
+      gemv_t(col(i), 1, dW_, &Hii);
+      tc = now_s();
+    }
     t_op += tb - ta;
     t_hii += tc - tb;
     H(i - 1, i) = H(i, i - 1);
     H(i, i) = Hii;
-    const uint32_t i1 = i + 1;
-    if (fused_) {
-      // f = w - H(i,i-1) v_{i-1} - Hii v_i, V'f and ||f|| in one pass over V[:, :i+1]
-      std::vector<double> hc(i1, 0.0);
-      hc[i] = Hii;
-      if (!restart) hc[i - 1] = H(i, i - 1);
-      beta = reorth_pass(i1, hc.data(), dW_, Vf.data());
-    } else {
+    if (!fused_) {
       k_resid<<<grid1d(256), 256, 0, stream_>>>(dW_, restart ? nullptr : col(i - 1), H(i, i - 1),
                                                 col(i), Hii, dF_, n_);
       beta = norm(dF_);
@@ -643,9 +693,7 @@ inline void Irlm::run(uint32_t maxit, double tol, IrlmResult& res) {
   alloc();
   nops_ = 0;
   // init(): v0 = SimpleRandom(0) normalised; w = A v0; H00 = v0.w; f = w - H00 v0
-  std::vector<double> r0;
-  simple_random_vec(r0, n_, 0);
-  cudaMemcpyAsync(dF_, r0.data(), sizeof(double) * n_, cudaMemcpyHostToDevice, stream_);
+  k_simple_random<<<grid1d(256), 256, 0, stream_>>>(dF_, n_, simple_random_r0(0));
   double vnorm = norm(dF_);
   k_scale2<<<grid1d(256), 256, 0, stream_>>>(1.0 / vnorm, dF_, col(0), dX_, n_);
   op_(dX_, dW_);
@@ -705,7 +753,7 @@ inline void Irlm::run(uint32_t maxit, double tol, IrlmResult& res) {
     res.conv[i] = conv[order_[i]];
   }
   if (getenv("FPB_IRLM_TRACE"))
-    fprintf(stderr, "[irlm] ops %u: enqueue-op %.1f ms, wait-op+Hii %.1f ms, reorth %.1f ms (%u passes)\n",
+    fprintf(stderr, "[irlm] ops %u: enqueue-op %.1f ms, wait-op + Hii + first pass %.1f ms, further passes %.1f ms (%u passes in all)\n",
             nops_, t_op * 1e3, t_hii * 1e3, t_reorth * 1e3, n_reorth);
   res.nconv = nconv;
   res.nops = nops_;
