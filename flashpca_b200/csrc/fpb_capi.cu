@@ -1665,6 +1665,7 @@ int fpb_perform_op_dev(fpb_handle* h, const double* d_x, double* d_y) {
   }
   FPB_CUDA(h, cudaGraphLaunch(it->second.exec, h->stream));
   h->launches += it->second.launches;
+  if (h->P.ok) h->P.used = true;  // the replayed op ends in the peer kernel: look at its watchdog word
   return 0;
 }
 
@@ -1676,8 +1677,14 @@ static int host_op(fpb_handle* h, const double* in, uint32_t k, double* out, uin
   if (in == out) FPB_FAIL(h, "input and output must not alias");
   FPB_CUDA(h, cudaSetDevice(h->device));
   if (ensure_staging(h, (size_t)in_rows * k, (size_t)out_rows * k)) return 1;
-  FPB_CUDA(h, cudaMemcpyAsync(h->d_in, in, sizeof(double) * in_rows * k, cudaMemcpyHostToDevice,
-                              h->stream));
+  static const bool slice_upload = !(getenv("FPB_SLICE_UPLOAD") && atoi(getenv("FPB_SLICE_UPLOAD")) == 0);
+  if (h->P.ok && slice_upload && dev_fn == fpb_perform_op_multi_dev) {
+    // perform_op's input is the same on every rank: upload a slice, gather the rest over NVLink
+    if (peer_upload_replicated(h, in, h->d_in, (size_t)in_rows * k)) return 1;
+  } else {
+    FPB_CUDA(h, cudaMemcpyAsync(h->d_in, in, sizeof(double) * in_rows * k, cudaMemcpyHostToDevice,
+                                h->stream));
+  }
   if (k == 1 && dev_fn == fpb_perform_op_multi_dev) {  // graph-replayed single-vector op
     if (fpb_perform_op_dev(h, h->d_in, h->d_out)) return 1;
   } else if (dev_fn(h, h->d_in, k, h->d_out)) {

@@ -132,7 +132,7 @@ int peer_allreduce(fpb_handle* h, double* d_buf, size_t count) {
   fpb_handle::Peer& P = h->P;
   for (size_t off = 0; off < count; off += P.cap) {
     const uint64_t len = std::min<uint64_t>(P.cap, count - off);
-    fpb::k_allreduce_peer<false><<<peer_grid(h), fpb::kPeerThreads, 0, h->stream>>>(
+    fpb::k_allreduce_peer<fpb::kPeerSum><<<peer_grid(h), fpb::kPeerThreads, 0, h->stream>>>(
         P.view, d_buf + off, nullptr, 0, 0, nullptr, nullptr, 0, 0, len, d_buf + off);
     h->launches++;
   }
@@ -143,12 +143,33 @@ int peer_allreduce(fpb_handle* h, double* d_buf, size_t count) {
 // k_finalize_prod + shard sum in one launch (single-vector second half)
 void peer_finalize_prod(fpb_handle* h, uint32_t nsplits, double* d_y) {
   fpb_handle::Peer& P = h->P;
-  fpb::k_allreduce_peer<true><<<peer_grid(h), fpb::kPeerThreads, 0, h->stream>>>(
+  fpb::k_allreduce_peer<fpb::kPeerFinalize><<<peer_grid(h), fpb::kPeerThreads, 0, h->stream>>>(
       P.view, nullptr, h->d_part, nsplits, h->part_stride, h->d_sc + 1,
       h->nmissing ? h->d_mc : nullptr, h->gtiles_i, h->n, h->n, d_y);
   h->launches++;
   P.used = true;
   P.summed = true;
+}
+
+// Host -> device copy of a vector (or N x k block) that every rank holds: each rank uploads only
+// its slice and the slices are exchanged over NVLink (all-gather through the result buffers) --
+// two GPUs share one PCIe uplink on an HGX board, NVLink is 15x wider.  d_dst receives all of it.
+int peer_upload_replicated(fpb_handle* h, const double* host_src, double* d_dst, size_t count) {
+  fpb_handle::Peer& P = h->P;
+  const uint64_t W = (uint64_t)P.view.world, r = (uint64_t)P.view.rank;
+  for (size_t off = 0; off < count; off += P.cap) {
+    const uint64_t len = std::min<uint64_t>(P.cap, count - off);
+    const uint64_t slice = (len + W - 1) / W;
+    const uint64_t lo = std::min<uint64_t>(r * slice, len), hi = std::min<uint64_t>(lo + slice, len);
+    if (hi > lo)
+      FPB_CUDA(h, cudaMemcpyAsync(d_dst + off + lo, host_src + off + lo, sizeof(double) * (hi - lo),
+                                  cudaMemcpyHostToDevice, h->stream));
+    fpb::k_allreduce_peer<fpb::kPeerGather><<<peer_grid(h), fpb::kPeerThreads, 0, h->stream>>>(
+        P.view, d_dst + off, nullptr, 0, 0, nullptr, nullptr, 0, 0, len, d_dst + off);
+    h->launches++;
+  }
+  P.used = true;
+  return 0;
 }
 
 int check_peer(fpb_handle* h) {  // after a synchronisation of the stream

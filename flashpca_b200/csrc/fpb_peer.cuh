@@ -88,13 +88,19 @@ __device__ __forceinline__ bool peer_barrier(const PeerView& pv, uint32_t* const
   return __syncthreads_and(ok);
 }
 
-// FUSED: phase 0 is k_finalize_prod (part / sc_ab / mcv as there); else phase 0 copies src.
-template <bool FUSED>
+// MODE kPeerSum:      phase 0 copies src into the exchange buffer, phase 1 sums over the ranks.
+// MODE kPeerFinalize: phase 0 is k_finalize_prod (part / sc_ab / mcv as there), phase 1 sums.
+// MODE kPeerGather:   all-gather -- src holds this rank's slice only (the host uploaded just that
+//                     part of a replicated vector); phase 1 stores it into every rank's result buffer.
+constexpr int kPeerSum = 0, kPeerFinalize = 1, kPeerGather = 2;
+
+template <int MODE>
 __global__ void __launch_bounds__(kPeerThreads, 1)
 k_allreduce_peer(PeerView pv, const double* __restrict__ src, const double* __restrict__ part,
                  uint32_t nsplits, uint64_t stride, const VecScale* __restrict__ sc_ab,
                  const double* __restrict__ mcv, uint32_t mc_tiles, uint64_t mc_stride,
                  uint64_t count, double* __restrict__ y) {
+  constexpr bool FUSED = MODE == kPeerFinalize;
   const int W = pv.world, r = pv.rank;
   const uint64_t slice = (count + W - 1) / W;                     // elements per rank
   const uint64_t sub = (slice + gridDim.x - 1) / gridDim.x;       // elements per (rank, CTA)
@@ -106,7 +112,7 @@ k_allreduce_peer(PeerView pv, const double* __restrict__ src, const double* __re
     sumb = sc_ab->sum;
   }
   // phase 0: the sub-slices (g, b) of the local partial sum
-  for (int g = 0; g < W; g++) {
+  for (int g = 0; MODE != kPeerGather && g < W; g++) {
     const uint64_t lo = g * slice + blockIdx.x * sub;
     const uint64_t hi = min(min(lo + sub, (g + 1) * slice), count);
     for (uint64_t i = lo + threadIdx.x; i < hi; i += kPeerThreads) {
@@ -128,19 +134,25 @@ k_allreduce_peer(PeerView pv, const double* __restrict__ src, const double* __re
     }
   }
   if (!peer_barrier(pv, pv.flag_a, e)) return;
-  // phase 1: sum sub-slice (r, b) over the ranks in rank order, store it everywhere
+  // phase 1: sum sub-slice (r, b) over the ranks in rank order (gather: take it from src), store it
+  // everywhere
   {
     const uint64_t lo = r * slice + blockIdx.x * sub;
     const uint64_t hi = min(min(lo + sub, (r + 1) * slice), count);
     for (uint64_t i = lo + threadIdx.x; i < hi; i += kPeerThreads) {
-      double v[kPeerMax];
+      double s;
+      if (MODE == kPeerGather) {
+        s = src[i];
+      } else {
+        double v[kPeerMax];
 #pragma unroll
-      for (int g = 0; g < kPeerMax; g++)
-        if (g < W) v[g] = peer_ld(pv.loc[g] + i);
-      double s = v[0];
+        for (int g = 0; g < kPeerMax; g++)
+          if (g < W) v[g] = peer_ld(pv.loc[g] + i);
+        s = v[0];
 #pragma unroll
-      for (int g = 1; g < kPeerMax; g++)
-        if (g < W) s += v[g];
+        for (int g = 1; g < kPeerMax; g++)
+          if (g < W) s += v[g];
+      }
 #pragma unroll
       for (int g = 0; g < kPeerMax; g++)
         if (g < W) pv.res[g][i] = s;

@@ -155,6 +155,9 @@ int fpb_comm_init(fpb_handle *h, const unsigned char id[128], int nranks, int ra
  * one kernel over NVLink peer memory, fused with the last step of the op (fixed summation order,
  * bit-identical on every rank), else as ncclAllReduce.  fpb_comm_kind: 0 = single shard,
  * 1 = ncclAllReduce, 2 = peer-memory kernel.  FPB_PEER=0 keeps NCCL.
+ * The host-pointer fpb_perform_op / fpb_perform_op_multi expect the same input on every rank (as the
+ * replicated Lanczos drivers provide it): with the peer-memory path each rank uploads only its
+ * slice of it and the slices are exchanged over NVLink (FPB_SLICE_UPLOAD=0: every rank uploads all).
  * fpb_comm_link_local links n handles of ONE process (shards on one GPU, or on GPUs with peer
  * access) as ranks 0..n-1 without NCCL; calls on the n handles must be issued concurrently
  * (one host thread per handle): each rank's kernel waits for the others. */
