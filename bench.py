@@ -4,7 +4,7 @@
 A "step" is one perform_op (y = X X' x, the body of one Arnoldi iteration,
 svdwide.cpp:21-68) over the whole synthetic 500,000 x 100,000 2-bit genotype
 matrix resident in HBM (BASELINE.json config 2/3), SNP-sharded over --gpus
-ranks with one NCCL all-reduce of y per step.
+ranks with one shard sum of y per step (the library's peer-memory kernel, else ncclAllReduce).
 
   value     N*P / t_step with x, y resident in HBM (CUDA events on the library's
             launch stream, max over ranks)
@@ -352,6 +352,7 @@ def run_b200(a):
         _lib.check(lib.fpb_sync(op.h), op.h)      # first collective of the library's communicator
         del y0, y1
     shard_sum = fdist.comm_kind(op)
+    slice_upload = shard_sum == "peer" and os.environ.get("FPB_SLICE_UPLOAD", "1") != "0"
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
@@ -371,7 +372,7 @@ def run_b200(a):
     k_ms = [t[0].item(), t[1].item()]        # the two halves, small kernels included
     g_ms = [t[2].item(), t[3].item()]        # the contraction kernel of each half alone
 
-    # ---- end to end through the host-pointer C ABI (H2D + op + all-reduce + D2H per step)
+    # ---- end to end through the host-pointer C ABI (H2D + op + shard sum + D2H per step)
     gen = torch.Generator(device="cpu").manual_seed(1234)
     x_host = torch.randn(n, dtype=torch.float64, generator=gen).pin_memory()
     y_host = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -554,7 +555,11 @@ def run_b200(a):
         "clocks": clocks,
         "e2e": {"value": n * p / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "median_ms_per_step": e2e_median,
-                "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                # per rank: with the peer-memory path a rank uploads its 1/world slice of x (the
+                # rest arrives over NVLink) and downloads all of y
+                "h2d_bytes_per_step": 8 * (-(-n // world)) if slice_upload else 8 * n,
+                "d2h_bytes_per_step": 8 * n,
+                "bytes_are": "per rank",
                 "y_norm": y_check},
         "gpu_launches": int(launches),
         "roofline": roofline,

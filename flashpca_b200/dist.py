@@ -1,6 +1,7 @@
 """SNP-sharded multi-GPU plumbing: one process per GPU, torch.distributed for
-rendezvous and host-side collectives; the per-op all-reduce itself runs inside
-the native library on its NCCL communicator (fpb_comm_init).
+rendezvous and host-side collectives; the per-op shard sum itself runs inside
+the native library (fpb_comm_init: a kernel over NVLink peer memory, csrc/fpb_peer.cuh,
+or ncclAllReduce on the library's communicator when peer memory cannot be mapped).
 
 X X' x = sum_g X_g X_g' x over disjoint contiguous SNP ranges -- the block sum
 of svdwide.cpp:48-59, distributed."""
