@@ -2,7 +2,7 @@
 //
 // The sharded op ends with y = sum_g y_g over the GPUs of the box (the block sum
 // of svdwide.cpp:48-59, distributed).  NCCL's all-reduce of the 4 MB vector costs 54 us on 8 GPUs,
-// half of it latency (profiles/r02_allreduce_probe_8gpu.txt).  k_allreduce_peer<true> does the
+// half of it latency (profiles/r02_allreduce_probe_8gpu.txt).  k_allreduce_peer<kPeerFinalize> does the
 // finalize step of the second half *and* the exchange in one launch:
 //
 //   phase 0  CTA b turns its share of the split partials into the local y_g (k_finalize_prod's
@@ -13,6 +13,10 @@
 //            NVSwitch) and stores the sum into every GPU's result buffer `res` (P2P stores),
 //   flag B   tells the peers the sub-slice has landed,
 //   phase 2  copies the sub-slices (g, b), all g, from `res` to the caller's y.
+//
+// (kPeerSum: phase 0 copies an existing vector instead -- block forms, other paths.  kPeerGather:
+// no phase 0 and phase 1 stores the rank's own slice instead of a sum -- the all-gather behind the
+// host-pointer perform_op, whose input every rank holds: each rank uploads 1/G of it over PCIe.)
 //
 // Every element is summed by exactly one rank in a fixed order, so all ranks hold bit-identical y
 // (the replicated Lanczos drivers must take identical decisions) and the result does not depend on
