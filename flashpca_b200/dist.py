@@ -85,3 +85,30 @@ def run_ranks(ops, fn):
         if e is not None:
             raise e
     return out
+
+
+def peer_partition(count: int, world: int, grid: int):
+    """Index arithmetic of the peer-memory shard sum (csrc/fpb_peer.cuh): rank r sums slice r =
+    [r S, (r+1) S) with S = ceil(count / world); CTA b of a rank handles sub-slice
+    [g S + b T, g S + (b+1) T) of every slice g, T = ceil(S / grid).  Returns
+    (slices, subs): slices[r] = (lo, hi), subs[g][b] = (lo, hi) (empty ranges have lo >= hi)."""
+    S = -(-count // world)
+    T = -(-S // grid)
+    slices = [(min(r * S, count), min((r + 1) * S, count)) for r in range(world)]
+    subs = [[(g * S + b * T, min(g * S + (b + 1) * T, (g + 1) * S, count)) for b in range(grid)]
+            for g in range(world)]
+    return slices, subs
+
+
+def two_shot_sum(parts):
+    """Host model of the kernel's result: every slice is summed by one rank over the ranks' partial
+    vectors in rank order and handed to all -- what every rank ends up holding."""
+    world, count = len(parts), parts[0].shape[0]
+    slices, _ = peer_partition(count, world, 1)
+    out = np.empty(count)
+    for lo, hi in slices:
+        acc = parts[0][lo:hi].copy()
+        for g in range(1, world):
+            acc += parts[g][lo:hi]
+        out[lo:hi] = acc
+    return out

@@ -30,6 +30,25 @@ yf = full.perform_op(x, 0)
 ok = np.abs(y.numpy() - yf).max() <= 1e-12 * np.abs(yf).max() and abs(tr.item() - full.trace) <= 1e-12 * full.trace
 msd = fdist.gather_meansd(local.meansd(), p, world, rank)
 ok = ok and np.array_equal(msd, full.meansd())
+# the library's own shard sum (csrc/fpb_peer.cuh) modelled on the host: every rank sees all partial
+# vectors (P2P loads), slice r is summed in rank order by rank r and handed to everybody (P2P stores)
+mine = torch.from_numpy(local.perform_op(x, 0))
+parts = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(parts, mine)
+slices, _ = fdist.peer_partition(n, world, 128)
+lo, hi = slices[rank]
+acc = parts[0][lo:hi].clone()
+for g in range(1, world):
+    acc += parts[g][lo:hi]
+S = slices[0][1] - slices[0][0]                      # gloo gathers equal sizes: pad the last slice
+pieces = [torch.empty(S, dtype=torch.float64) for _ in slices]
+dist.all_gather(pieces, torch.cat([acc, torch.zeros(S - acc.numel(), dtype=torch.float64)]))
+y2 = torch.cat([q[: s[1] - s[0]] for q, s in zip(pieces, slices)]).numpy()
+ok = ok and np.array_equal(y2, fdist.two_shot_sum([q.numpy() for q in parts]))
+ok = ok and np.abs(y2 - yf).max() <= 1e-12 * np.abs(yf).max()
+ref = torch.from_numpy(y2.copy())
+dist.broadcast(ref, src=0)
+ok = ok and np.array_equal(ref.numpy(), y2)          # bit-identical on every rank
 flag = torch.tensor([1 if ok else 0])
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0 and flag.item() == 1:

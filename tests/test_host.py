@@ -165,6 +165,28 @@ def test_two_rank_gloo_shard_sum():
     assert "SHARD_OK" in out.stdout
 
 
+def test_peer_partition_covers_every_element_once():
+    """The (rank, CTA) sub-slices of the peer-memory shard sum (index arithmetic of
+    csrc/fpb_peer.cuh, mirrored by flashpca_b200.dist.peer_partition) tile [0, count) exactly:
+    ragged counts, fewer elements than CTAs, one rank."""
+    from flashpca_b200 import dist as fdist
+    for count in (1, 7, 957, 20011, 500000, 4000003):
+        for world in (1, 2, 3, 8):
+            for grid in (32, 128):
+                slices, subs = fdist.peer_partition(count, world, grid)
+                cover = np.zeros(count, dtype=np.int32)
+                for g in range(world):
+                    for lo, hi in subs[g]:
+                        if hi > lo:
+                            assert slices[g][0] <= lo and hi <= slices[g][1]
+                            cover[lo:hi] += 1
+                assert (cover == 1).all(), (count, world, grid)
+                assert slices[0][0] == 0 and max(s[1] for s in slices) == count
+    rng = np.random.default_rng(0)
+    parts = [rng.standard_normal(1001) for _ in range(3)]
+    assert np.array_equal(fdist.two_shot_sum(parts), (parts[0] + parts[1]) + parts[2])
+
+
 def test_cli_argument_validation_runs_without_gpu(native_lib, tmp_path):
     """The flashpca front end validates options before it touches the device
     (messages and exit codes of flashpca.cpp:94-564)."""
